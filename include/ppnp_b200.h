@@ -1,0 +1,190 @@
+/*
+ * ppnp_b200.h -- C ABI of libppnp_b200.so: the PPNP/APPNP propagation hot path of
+ * bkj/ppnp as hand-written CUDA for sm_100a (B200).
+ *
+ * The reference is pure Python; there is no FFI in it.  Each entry point below
+ * replaces the reference expression cited next to it (paths are relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     name ends in _host; the caller owns every buffer (the library never
+ *     allocates or frees caller-visible memory and keeps no global device state);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing
+ *     synchronises the device unless stated;
+ *   - return 0 on success, a negative PPNP_E* code on failure; the message of the
+ *     last failure on the calling thread is ppnp_last_error(); nothing throws.
+ */
+#ifndef PPNP_B200_H
+#define PPNP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPNP_OK 0
+#define PPNP_EINVAL (-1)   /* bad argument (shape, alignment, null pointer)  */
+#define PPNP_ECUDA (-2)    /* a CUDA runtime call or a launch failed          */
+#define PPNP_ENOTSUP (-3)  /* configuration not supported by this build       */
+
+/* normalisation modes of helpers.py:58-66 calc_A_hat(adj, mode) */
+#define PPNP_MODE_SYM 0    /* D^-1/2 (A+I) D^-1/2   helpers.py:61-63 */
+#define PPNP_MODE_RW 1     /* D^-1 (A+I)            helpers.py:64-66 */
+
+/* epilogue of one propagation step, out[r] = a(deg_r) * acc_r + b(deg_r) * T[r] */
+#define PPNP_EPI_PLAIN 0   /* a = 1-alpha,            b = alpha            stored values, Z-space         */
+#define PPNP_EPI_Z2Y 1     /* a = (1-alpha)/sqrt(d),  b = alpha/sqrt(d)    stored values, first step Z->Y  */
+#define PPNP_EPI_Y 2       /* a = (1-alpha)/d,        b = alpha/sqrt(d)    value-free, Y = D^-1/2 Z space  */
+#define PPNP_EPI_Y2Z 3     /* a = (1-alpha)/sqrt(d),  b = alpha            value-free, last step Y->Z      */
+#define PPNP_EPI_RW 4      /* a = (1-alpha)/d,        b = alpha            value-free 'rw' mode            */
+
+/* bit 31 of a stream column: last edge of its segment; of a seg_row entry: partial segment */
+#define PPNP_FLAG 0x80000000u
+#define PPNP_NULL_COL 0x7fffffff /* padding edge: contributes nothing */
+
+const char* ppnp_last_error(void);
+int ppnp_version(void);
+/* SM count, compute capability and L2 size of the current device. */
+int ppnp_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* l2_bytes);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) CSR build + normalisation.                      replaces helpers.py:58-66 calc_A_hat
+ *
+ * in : canonical CSR of adj (sparsegraph.py:191-222 standardize): indptr int32[n+1],
+ *      indices int32[nnz] sorted per row, data fp32[nnz] or NULL (= all ones).
+ * out: structure of A = adj + I (helpers.py:59; the diagonal is merged in sorted position,
+ *      an existing diagonal entry gets +1), bit-exact with scipy:
+ *        out_indptr int32[n+1], out_indices int32[cap >= nnz+n],
+ *        out_deg    fp64[n]   D = rowsum(A)                        (helpers.py:60)
+ *        out_val64  fp64[cap] (D_i^-1/2 a_ij) D_j^-1/2 in that order, or (1/D_i) a_ij   (nullable)
+ *        out_val32  fp32[cap] the same value rounded once to fp32                        (nullable)
+ *        out_dinv   fp32[n]   D^-1/2 ('sym') or D^-1 ('rw') rounded to fp32              (nullable)
+ * workspace: ppnp_csr_normalize_workspace_bytes(n) bytes.
+ * ---------------------------------------------------------------------------------------- */
+int64_t ppnp_csr_normalize_workspace_bytes(int64_t n);
+int ppnp_csr_normalize(const int32_t* indptr, const int32_t* indices, const float* data,
+                       int64_t n, int64_t nnz, int32_t mode,
+                       int32_t* out_indptr, int32_t* out_indices, double* out_deg,
+                       double* out_val64, float* out_val32, float* out_dinv,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) APPNP propagation.        Z_{k+1} = (1-alpha) A_hat Z_k + alpha H, Z_0 = H   (north_star;
+ *     the reference holds only the K->inf limit, model.py:63 with helpers.py:68-71)
+ *
+ * The adjacency is consumed as an "edge stream" (ppnp_b200/plan.py builds it from the
+ * normalised CSR): the rows of A_hat in processing order, cut into segments that never cross
+ * a chunk of `chunk_edges` edges.  cols[e] = column | PPNP_FLAG on the last edge of a
+ * segment, PPNP_NULL_COL for padding; seg_row[s] = row the segment finishes, or
+ * PPNP_FLAG | slot when the row is split over several segments (the partial sums go to
+ * partial[slot] and ppnp_spmm_fixup adds them up in slot order -- deterministic);
+ * chunk_seg[c] = index of the first segment of chunk c.  vals (nullable) are the stored
+ * values of A_hat in stream order; without them every edge has weight 1 (value-free form,
+ * SURVEY.md section 8d) and the row scaling is done by the epilogue from the row degree.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ppnp_plan {
+    int64_t n;              /* rows                                                     */
+    int64_t n_edges;        /* stream length, multiple of chunk_edges                   */
+    int64_t n_chunks;       /* n_edges / chunk_edges, multiple of 32                    */
+    int64_t n_segs;
+    int64_t n_fix;          /* rows split over several segments                         */
+    int64_t n_slots;        /* partial segments                                          */
+    int32_t chunk_edges;    /* edges per chunk (multiple of 128)                        */
+    int32_t reserved;
+    const int32_t* cols;      /* [n_edges]                                              */
+    const float* vals;        /* [n_edges] or NULL                                      */
+    const int32_t* seg_row;   /* [n_segs]                                               */
+    const int32_t* chunk_seg; /* [n_chunks]                                             */
+    const int32_t* fix_ptr;   /* [n_fix + 1] slot ranges                                */
+    const int32_t* fix_row;   /* [n_fix]                                                */
+    const float* fix_deg;     /* [n_fix] row degree (edge count incl. self loop)        */
+} ppnp_plan_t;
+
+/* One step: out = a * (A_hat-or-(A+I)) Zin + b * T with the epilogue `epi`.
+ * Zin, T, Zout: n x F fp32 row-major with leading dimension ld (floats); Zout must not alias
+ * Zin.  partial: n_slots x ld floats (may be NULL when n_slots == 0). use_vals != 0 selects the
+ * stored-value form (plan->vals must be set). */
+int ppnp_spmm_step(const ppnp_plan_t* plan, const float* Zin, const float* T, float* Zout,
+                   float* partial, int64_t ld, int32_t F, float alpha, int32_t epi,
+                   int32_t use_vals, void* stream);
+
+/* K steps from Z_0 = H.  mode PPNP_MODE_SYM: value-free Y-space iteration when plan->vals is
+ * given only for the first step (use_vals == 0), stored values every step when use_vals != 0.
+ * Result in Z (n x ld); scratch is a second n x ld buffer; partial as above.
+ * Used for the forward AND the backward pass (A_hat symmetric). */
+int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, float* scratch,
+                         float* partial, int64_t ld, int32_t F, int32_t K, float alpha,
+                         int32_t mode, int32_t use_vals, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Exact PPNP.                                      replaces helpers.py:68-71 compute_ppr
+ *     Pi = alpha (I - (1-alpha) A_hat)^-1 by power iteration on all n right-hand sides:
+ *     Pi_0 = I, Pi_{k+1} = (1-alpha) A_hat Pi_k + alpha I.   A_hat: normalised CSR with fp32
+ *     values (output of ppnp_csr_normalize).  Pi, scratch: n x n fp32 row-major.  Result in Pi.
+ * ---------------------------------------------------------------------------------------- */
+int ppnp_ppr_dense(const int32_t* indptr, const int32_t* indices, const float* val,
+                   int64_t n, float alpha, int32_t K, float* Pi, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3b) Dense apply.                 replaces model.py:63  self.ppr[idx] @ H   (idx != NULL)
+ *                                   and      model.py:65  ppr @ H             (idx == NULL)
+ *      out[m x C] = op(Pi)[idx, :] @ H[n x C]; Pi is m_pi x n row-major (ld_pi elements).
+ *      transpose != 0 computes the autograd adjoint  out[n x C] = Pi[idx, :]^T @ H[m x C].
+ *      ppnp_gather_gemm_f32 : fp32 SIMT, the 1e-5 parity path.
+ *      ppnp_gather_gemm_bf16: Pi in bf16, H converted to bf16 on the fly, fp32 accumulation
+ *                             in TMEM via tcgen05.mma (the 1e-2 path).  workspace from
+ *                             ppnp_gather_gemm_bf16_workspace_bytes.
+ * ---------------------------------------------------------------------------------------- */
+int ppnp_gather_gemm_f32(const float* Pi, int64_t ld_pi, const int64_t* idx, int64_t m, int64_t n,
+                         const float* H, int64_t ld_h, int32_t C, float* out, int64_t ld_out,
+                         int32_t transpose, void* stream);
+int64_t ppnp_gather_gemm_bf16_workspace_bytes(int64_t m, int64_t n, int32_t C);
+int ppnp_gather_gemm_bf16(const void* Pi_bf16, int64_t ld_pi, const int64_t* idx, int64_t m,
+                          int64_t n, const float* H, int64_t ld_h, int32_t C, float* out,
+                          int64_t ld_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* fp32 -> bf16 (round to nearest even) copy used to build the bf16 shadow of Pi. */
+int ppnp_f32_to_bf16(const float* src, void* dst_bf16, int64_t count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) batch-main.py path.
+ *   ppnp_topk_thresh : batch-main.py:115  thresh, _ = ppr.topk(k, axis=-1); thresh[:, -1]
+ *                      k-th largest of every row of the dense n_rows x n_cols fp32 matrix (bit-exact
+ *                      selection, no sorting of the row).
+ *   ppnp_topk_mask   : batch-main.py:116  ppr[ppr < thresh[:, -1]] = 0   (in place; entry (i, j)
+ *                      is compared with thresh[j] -- the reference's broadcast)
+ *   ppnp_dense_row_nnz / ppnp_dense_to_csr: compact the masked matrix (entries > 0) to CSR.
+ *   ppnp_batch_support: batch-main.py:140-141  sel = (ppr[idx_batch] > 0).any(0) on the compact
+ *                      form: mark[j] = 1 for every column in the support of the batch rows.
+ *   ppnp_batch_propagate: batch-main.py:142-146  logits = ppr[idx_batch][:, sel] @ Hsub where
+ *                      Hsub = encoder(X[sel]); colmap[j] = position of column j in sel.
+ *                      transpose != 0: the autograd adjoint dHsub = ppr_sub^T @ dlogits
+ *                      (dHsub must be zeroed by the caller; accumulated with atomics).
+ * ---------------------------------------------------------------------------------------- */
+int ppnp_topk_thresh(const float* ppr, int64_t n_rows, int64_t n_cols, int64_t ld, int32_t k,
+                     float* thresh, void* stream);
+int ppnp_topk_mask(float* ppr, int64_t n_rows, int64_t n_cols, int64_t ld, const float* thresh,
+                   void* stream);
+int ppnp_dense_row_nnz(const float* ppr, int64_t n_rows, int64_t n_cols, int64_t ld,
+                       int32_t* row_nnz, void* stream);
+int ppnp_dense_to_csr(const float* ppr, int64_t n_rows, int64_t n_cols, int64_t ld,
+                      const int64_t* indptr, int32_t* indices, float* val, void* stream);
+int ppnp_batch_support(const int64_t* indptr, const int32_t* indices, const int64_t* idx_batch,
+                       int64_t B, uint8_t* mark, void* stream);
+int ppnp_batch_propagate(const int64_t* indptr, const int32_t* indices, const float* val,
+                         const int64_t* idx_batch, int64_t B, const int32_t* colmap,
+                         const float* Hsub, int64_t ld_h, int32_t C, float* out, int64_t ld_out,
+                         int32_t transpose, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic-workload plumbing (BASELINE.json configs 4/5): R-MAT raw draws e0..e1 of stream
+ * `seed` (include/ppnp_rmat.h), written as 64-bit keys (src << 32 | dst), both directions,
+ * loops and ids >= n replaced by the key -1.  out_keys has 2 * (e1 - e0) entries.
+ * ---------------------------------------------------------------------------------------- */
+int ppnp_rmat_keys(uint64_t seed, int32_t scale, int64_t n, int64_t e0, int64_t e1,
+                   int64_t* out_keys, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPNP_B200_H */

@@ -1,0 +1,65 @@
+"""Build libppnp_b200.so (all csrc/*.cu, sm_100a only) in-tree with nvcc."""
+import glob
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+OUT = os.path.join(_HERE, "libppnp_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; the CUDA library cannot be built")
+    return cand
+
+
+def _stale(sources):
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = sources + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(_HERE, "..", "include", "*.h"))
+    return any(os.path.getmtime(s) > t for s in deps)
+
+
+def build_library(force=False, verbose=False):
+    sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    if not sources:
+        raise RuntimeError("no CUDA sources found")
+    if not force and not _stale(sources):
+        return OUT
+    objdir = os.path.join(_HERE, "csrc", "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    objs, procs = [], []
+    for s in sources:
+        o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for s, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {os.path.basename(s)}\n{out}")
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
+    cmd = [nvcc, "-shared", "-o", OUT, *objs, "-lcuda"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    with open(os.path.join(objdir, "build.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

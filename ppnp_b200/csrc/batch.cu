@@ -1,0 +1,122 @@
+// batch.cu -- batch-main.py's per-batch gather / propagate on the compact top-k PPR matrix.
+//
+//   batch-main.py:140  ppr_sub = model.ppr[idx_batch]          B x n dense gather         |
+//   batch-main.py:141  sel = (ppr_sub > 0).any(dim=0)          support union              | -> batch_support_kernel
+//   batch-main.py:142  ppr_sub = ppr_sub[:, sel]               column compaction          |    (marks only)
+//   batch-main.py:146  logits = ppr_sub @ encoder(X[sel])      model.py:65                  -> batch_propagate_kernel
+// The reference reads 3 * B * n * 4 bytes of mostly-zero rows per batch; here a batch touches the
+// nnz of its rows once (8 B per kept entry) plus the m x C block of encoder outputs.
+#include "common.cuh"
+
+namespace ppnp {
+namespace {
+
+// one warp per batch row: mark the columns it keeps
+__global__ void __launch_bounds__(256)
+batch_support_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                     const int64_t* __restrict__ idx_batch, int64_t B, uint8_t* __restrict__ mark) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= B) return;
+    const int64_t r = idx_batch[w];
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    for (int64_t t = b + lane; t < e; t += 32) mark[__ldg(indices + t)] = 1;
+}
+
+// one warp per batch row; G lanes share one kept entry (G = pow2 >= C chunk), 32/G entries in flight
+template <int G>
+__global__ void __launch_bounds__(256)
+batch_propagate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                       const float* __restrict__ val, const int64_t* __restrict__ idx_batch, int64_t B,
+                       const int32_t* __restrict__ colmap, const float* __restrict__ Hsub, int64_t ld_h, int C,
+                       float* __restrict__ out, int64_t ld_out) {
+    constexpr int EPW = 32 / G;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= B) return;
+    const int sub = lane / G, lc = lane % G;
+    const int64_t r = idx_batch[w];
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    for (int c0 = 0; c0 < C; c0 += G) {
+        const int c = c0 + lc;
+        float acc = 0.f;
+        for (int64_t t = b + sub; t < e; t += EPW) {
+            const int col = __ldg(indices + t);
+            const float v = __ldg(val + t);
+            const int pos = __ldg(colmap + col);
+            if (c < C) acc = fmaf(v, __ldg(Hsub + (int64_t)pos * ld_h + c), acc);
+        }
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sub == 0 && c < C) out[w * ld_out + c] = acc;
+    }
+}
+
+// adjoint: dHsub[colmap[col], :] += val * dlogits[b, :]
+template <int G>
+__global__ void __launch_bounds__(256)
+batch_propagate_t_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                         const float* __restrict__ val, const int64_t* __restrict__ idx_batch, int64_t B,
+                         const int32_t* __restrict__ colmap, const float* __restrict__ dlogits, int64_t ld_g, int C,
+                         float* __restrict__ dH, int64_t ld_dh) {
+    constexpr int EPW = 32 / G;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= B) return;
+    const int sub = lane / G, lc = lane % G;
+    const int64_t r = idx_batch[w];
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    for (int c0 = 0; c0 < C; c0 += G) {
+        const int c = c0 + lc;
+        const float g = (c < C) ? __ldg(dlogits + w * ld_g + c) : 0.f;
+        for (int64_t t = b + sub; t < e; t += EPW) {
+            const int col = __ldg(indices + t);
+            const float v = __ldg(val + t);
+            const int pos = __ldg(colmap + col);
+            if (c < C) atomicAdd(dH + (int64_t)pos * ld_dh + c, v * g);
+        }
+    }
+}
+
+}  // namespace
+}  // namespace ppnp
+
+extern "C" {
+
+int ppnp_batch_support(const int64_t* indptr, const int32_t* indices, const int64_t* idx_batch, int64_t B,
+                       uint8_t* mark, void* stream) {
+    using namespace ppnp;
+    PPNP_REQUIRE(indptr && indices && idx_batch && mark, "null pointer");
+    PPNP_REQUIRE(B > 0, "B > 0");
+    batch_support_kernel<<<(unsigned)((B + 7) / 8), 256, 0, as_stream(stream)>>>(indptr, indices, idx_batch, B, mark);
+    PPNP_CHECK_LAUNCH("batch_support_kernel");
+    return PPNP_OK;
+}
+
+int ppnp_batch_propagate(const int64_t* indptr, const int32_t* indices, const float* val, const int64_t* idx_batch,
+                         int64_t B, const int32_t* colmap, const float* Hsub, int64_t ld_h, int32_t C, float* out,
+                         int64_t ld_out, int32_t transpose, void* stream_) {
+    using namespace ppnp;
+    PPNP_REQUIRE(indptr && indices && val && idx_batch && colmap && Hsub && out, "null pointer");
+    PPNP_REQUIRE(B > 0 && C > 0 && ld_h >= C && ld_out >= C, "bad shape");
+    cudaStream_t stream = as_stream(stream_);
+    const unsigned grid = (unsigned)((B + 7) / 8);
+#define PPNP_BP(G_)                                                                                                    \
+    do {                                                                                                               \
+        if (!transpose)                                                                                                \
+            batch_propagate_kernel<G_><<<grid, 256, 0, stream>>>(indptr, indices, val, idx_batch, B, colmap, Hsub,     \
+                                                                 ld_h, C, out, ld_out);                                \
+        else                                                                                                           \
+            batch_propagate_t_kernel<G_><<<grid, 256, 0, stream>>>(indptr, indices, val, idx_batch, B, colmap, Hsub,   \
+                                                                   ld_h, C, out, ld_out);                              \
+    } while (0)
+    if (C <= 4) PPNP_BP(4);
+    else if (C <= 8) PPNP_BP(8);
+    else if (C <= 16) PPNP_BP(16);
+    else PPNP_BP(32);
+#undef PPNP_BP
+    PPNP_CHECK_LAUNCH("batch_propagate_kernel");
+    return PPNP_OK;
+}
+
+}  // extern "C"

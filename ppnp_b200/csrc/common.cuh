@@ -1,0 +1,99 @@
+// common.cuh -- error plumbing and small device helpers shared by every kernel file.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ppnp_b200.h"
+
+namespace ppnp {
+
+void set_error(const char* fmt, ...);
+
+inline int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return PPNP_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return PPNP_ECUDA;
+}
+
+#define PPNP_CHECK_LAUNCH(name)                                             \
+    do {                                                                    \
+        int rc__ = ::ppnp::check_cuda(cudaGetLastError(), "launch " name);  \
+        if (rc__ != PPNP_OK) return rc__;                                   \
+    } while (0)
+
+#define PPNP_REQUIRE(cond, msg)                                             \
+    do {                                                                    \
+        if (!(cond)) {                                                      \
+            ::ppnp::set_error("%s: requirement failed: %s", __func__, msg); \
+            return PPNP_EINVAL;                                             \
+        }                                                                   \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();
+
+// ---- streaming (evict-first) loads / stores: index, teleport and output streams must not
+// ---- push the gathered Z rows out of L2.
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+__device__ __forceinline__ int4 ld_stream(const int4* p) { return __ldcs(p); }
+__device__ __forceinline__ int2 ld_stream(const int2* p) { return __ldcs(p); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+template <int N>
+struct Vec;
+template <>
+struct Vec<1> {
+    float x;
+    __device__ __forceinline__ void zero() { x = 0.f; }
+    __device__ __forceinline__ void add(const Vec& o) { x += o.x; }
+    __device__ __forceinline__ void fma(float w, const Vec& o) { x = fmaf(w, o.x, x); }
+    __device__ __forceinline__ static Vec load(const float* p) { Vec v; v.x = __ldg(p); return v; }
+    __device__ __forceinline__ static Vec load_plain(const float* p) { Vec v; v.x = *p; return v; }
+    __device__ __forceinline__ static Vec load_stream(const float* p) { Vec v; v.x = __ldcs(p); return v; }
+    __device__ __forceinline__ void store(float* p) const { *p = x; }
+    __device__ __forceinline__ void store_stream(float* p) const { __stcs(p, x); }
+    __device__ __forceinline__ static Vec axpby(float a, const Vec& u, float b, const Vec& v) {
+        Vec r; r.x = fmaf(a, u.x, b * v.x); return r;
+    }
+};
+template <>
+struct Vec<4> {
+    float4 v;
+    __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void add(const Vec& o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+    __device__ __forceinline__ void fma(float w, const Vec& o) {
+        v.x = fmaf(w, o.v.x, v.x); v.y = fmaf(w, o.v.y, v.y); v.z = fmaf(w, o.v.z, v.z); v.w = fmaf(w, o.v.w, v.w);
+    }
+    __device__ __forceinline__ static Vec load(const float* p) { Vec r; r.v = __ldg(reinterpret_cast<const float4*>(p)); return r; }
+    __device__ __forceinline__ static Vec load_plain(const float* p) { Vec r; r.v = *reinterpret_cast<const float4*>(p); return r; }
+    __device__ __forceinline__ static Vec load_stream(const float* p) { Vec r; r.v = __ldcs(reinterpret_cast<const float4*>(p)); return r; }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+    __device__ __forceinline__ void store_stream(float* p) const { __stcs(reinterpret_cast<float4*>(p), v); }
+    __device__ __forceinline__ static Vec axpby(float a, const Vec& u, float b, const Vec& w) {
+        Vec r;
+        r.v.x = fmaf(a, u.v.x, b * w.v.x); r.v.y = fmaf(a, u.v.y, b * w.v.y);
+        r.v.z = fmaf(a, u.v.z, b * w.v.z); r.v.w = fmaf(a, u.v.w, b * w.v.w);
+        return r;
+    }
+};
+
+// epilogue coefficients, out = a * acc + b * teleport   (include/ppnp_b200.h PPNP_EPI_*)
+__device__ __forceinline__ void epi_coef(int epi, float alpha, float deg, float& a, float& b) {
+    const float oma = 1.0f - alpha;
+    switch (epi) {
+        default:
+        case PPNP_EPI_PLAIN: a = oma; b = alpha; break;
+        case PPNP_EPI_Z2Y: { const float d = 1.0f / sqrtf(deg); a = oma * d; b = alpha * d; } break;
+        case PPNP_EPI_Y: a = oma / deg; b = alpha / sqrtf(deg); break;
+        case PPNP_EPI_Y2Z: a = oma / sqrtf(deg); b = alpha; break;
+        case PPNP_EPI_RW: a = oma / deg; b = alpha; break;
+    }
+}
+
+}  // namespace ppnp

@@ -1,0 +1,393 @@
+"""Host-side operators over libppnp_b200.so.  Tensors in, tensors out; every op runs on the
+current CUDA stream and raises when the CUDA library is missing (no fallback path).
+
+Reference lines each operator replaces are cited per function (paths into the reference tree).
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .plan import StreamPlan, build_stream_plan, degree_order
+
+MODE = {"sym": _lib.MODE_SYM, "rw": _lib.MODE_RW}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("ppnp_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+@dataclass
+class NormalizedCSR:
+    """A_hat of helpers.py:58-66 on the device: structure of adj + I, D, values, D^-1/2."""
+    n: int
+    nnz: int
+    indptr: torch.Tensor     # int32 [n+1]
+    indices: torch.Tensor    # int32 [nnz]
+    deg: torch.Tensor        # fp64 [n]   D = rowsum(adj + I)
+    val64: Optional[torch.Tensor]  # fp64 [nnz]
+    val32: Optional[torch.Tensor]  # fp32 [nnz]
+    dinv: torch.Tensor       # fp32 [n]
+    mode: str
+
+
+def csr_normalize(indptr, indices, data=None, mode="sym", want_val64=False, want_val32=True):
+    """helpers.py:58-66 ``calc_A_hat(adj, mode)`` on the GPU.
+
+    indptr/indices: canonical CSR of ``adj`` (int32, sorted, CUDA tensors); data: fp32 weights or
+    None for the all-ones adjacency that ``SparseGraph.standardize`` produces.
+    """
+    lib = _lib.load()
+    _require_cuda(indptr, indices, data)
+    indptr = indptr.to(torch.int32).contiguous()
+    indices = indices.to(torch.int32).contiguous()
+    if data is not None:
+        data = data.to(torch.float32).contiguous()
+    n = indptr.numel() - 1
+    nnz = indices.numel()
+    dev = indices.device
+    cap = nnz + n
+    out_indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    out_indices = torch.empty(cap, dtype=torch.int32, device=dev)
+    out_deg = torch.empty(n, dtype=torch.float64, device=dev)
+    out_val64 = torch.empty(cap, dtype=torch.float64, device=dev) if want_val64 else None
+    out_val32 = torch.empty(cap, dtype=torch.float32, device=dev) if want_val32 else None
+    out_dinv = torch.empty(n, dtype=torch.float32, device=dev)
+    ws_bytes = lib.ppnp_csr_normalize_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ppnp_csr_normalize(_lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data), n, nnz, MODE[mode],
+                                    _lib.ptr(out_indptr), _lib.ptr(out_indices), _lib.ptr(out_deg),
+                                    _lib.ptr(out_val64), _lib.ptr(out_val32), _lib.ptr(out_dinv),
+                                    _lib.ptr(ws), ws_bytes, _lib.current_stream())
+    _lib.check(rc, "ppnp_csr_normalize")
+    nnz_hat = int(out_indptr[-1].item())
+    return NormalizedCSR(n=n, nnz=nnz_hat, indptr=out_indptr, indices=out_indices[:nnz_hat], deg=out_deg,
+                         val64=None if out_val64 is None else out_val64[:nnz_hat],
+                         val32=None if out_val32 is None else out_val32[:nnz_hat], dinv=out_dinv, mode=mode)
+
+
+class PropagationGraph:
+    """Normalised adjacency + edge-stream plan, ready for ``appnp_propagate``."""
+
+    def __init__(self, ahat: NormalizedCSR, chunk_edges=256, order="natural", keep_vals=True):
+        self.ahat = ahat
+        self.mode = ahat.mode
+        if order == "natural":
+            ord_t = None
+        elif order == "degree":
+            ord_t = degree_order(ahat.indptr)
+        elif torch.is_tensor(order):
+            ord_t = order
+        else:
+            raise ValueError(f"unknown order {order!r}")
+        vals = ahat.val32 if keep_vals else None
+        self.plan: StreamPlan = build_stream_plan(ahat.indptr, ahat.indices, vals, chunk_edges, ord_t)
+        self.n = ahat.n
+        self.nnz = ahat.nnz
+        self._partial = {}
+
+    @classmethod
+    def from_adjacency(cls, indptr, indices, data=None, mode="sym", **kw):
+        return cls(csr_normalize(indptr, indices, data, mode), **kw)
+
+    def partial_buffer(self, ld):
+        if self.plan.n_slots == 0:
+            return None
+        buf = self._partial.get(ld)
+        if buf is None:
+            buf = torch.empty(self.plan.n_slots * ld, dtype=torch.float32, device=self.plan.device)
+            self._partial[ld] = buf
+        return buf
+
+
+def spmm_step(graph: PropagationGraph, Zin, T, alpha, epi=_lib.EPI_PLAIN, use_vals=True, out=None):
+    """One propagation step  out = a * A Zin + b * T  (epilogue ``epi``, include/ppnp_b200.h)."""
+    lib = _lib.load()
+    _require_cuda(Zin, T)
+    Zin = Zin.contiguous()
+    T = T.contiguous()
+    n, F = Zin.shape
+    if out is None:
+        out = torch.empty_like(Zin)
+    partial = graph.partial_buffer(F)
+    with torch.cuda.device(Zin.device):
+        rc = lib.ppnp_spmm_step(graph.plan.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), _lib.ptr(partial),
+                                F, F, float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
+    _lib.check(rc, "ppnp_spmm_step")
+    return out
+
+
+def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False, out=None, scratch=None):
+    """K steps of Z <- (1-alpha) A_hat Z + alpha H from Z_0 = H (north_star; forward and backward).
+
+    ``use_vals=False`` runs the value-free Y-space iteration (stored values only in step 1),
+    ``use_vals=True`` multiplies by the stored A_hat values in every step.
+    """
+    lib = _lib.load()
+    _require_cuda(H)
+    if H.dtype != torch.float32 or H.dim() != 2:
+        raise ValueError("H must be a 2-D float32 tensor")
+    H = H.contiguous()
+    n, F = H.shape
+    if n != graph.n:
+        raise ValueError(f"H has {n} rows, graph has {graph.n}")
+    if K == 0:
+        return H.clone()
+    Z = out if out is not None else torch.empty_like(H)
+    scratch = scratch if scratch is not None else torch.empty_like(H)
+    partial = graph.partial_buffer(F)
+    with torch.cuda.device(H.device):
+        rc = lib.ppnp_appnp_propagate(graph.plan.struct(), _lib.ptr(H), _lib.ptr(Z), _lib.ptr(scratch),
+                                      _lib.ptr(partial), F, F, int(K), float(alpha), MODE[graph.mode],
+                                      int(bool(use_vals)), _lib.current_stream())
+    _lib.check(rc, "ppnp_appnp_propagate")
+    return Z
+
+
+class _APPNPFunction(torch.autograd.Function):
+    """dH = P_K(A_hat) dZ: the same K-step kernel on the upstream gradient (A_hat symmetric,
+    SURVEY.md section 3.3) -- no activations are saved."""
+
+    @staticmethod
+    def forward(ctx, H, graph, K, alpha, use_vals):
+        ctx.graph, ctx.K, ctx.alpha, ctx.use_vals = graph, K, alpha, use_vals
+        return appnp_propagate(graph, H, K, alpha, use_vals)
+
+    @staticmethod
+    def backward(ctx, gZ):
+        if ctx.graph.mode != "sym":
+            raise RuntimeError("backward is implemented for the symmetric normalisation only")
+        return appnp_propagate(ctx.graph, gZ.contiguous(), ctx.K, ctx.alpha, ctx.use_vals), None, None, None, None
+
+
+def appnp(H, graph, K=10, alpha=0.1, use_vals=False):
+    """Differentiable APPNP propagation."""
+    return _APPNPFunction.apply(H, graph, K, alpha, use_vals)
+
+
+# ------------------------------------------------------------------------------ exact PPNP
+def ppr_steps_for_tol(alpha, tol):
+    """Steps for the power iteration to reach spectral-norm error ``tol``: (1-alpha)^K <= tol."""
+    import math
+    return max(1, int(math.ceil(math.log(tol) / math.log(1.0 - alpha))))
+
+
+def ppr_dense(ahat: NormalizedCSR, alpha, K=None, tol=1e-7):
+    """helpers.py:68-71 ``compute_ppr``: Pi = alpha (I - (1-alpha) A_hat)^-1 as a dense fp32 n x n
+    CUDA tensor, by power iteration on all n right-hand sides (csrc/ppr_dense.cu)."""
+    lib = _lib.load()
+    if ahat.val32 is None:
+        raise ValueError("ppr_dense needs the fp32 values of A_hat")
+    n = ahat.n
+    K = ppr_steps_for_tol(alpha, tol) if K is None else int(K)
+    dev = ahat.indices.device
+    Pi = torch.empty((n, n), dtype=torch.float32, device=dev)
+    scratch = torch.empty((n, n), dtype=torch.float32, device=dev) if K > 1 else None
+    with torch.cuda.device(dev):
+        rc = lib.ppnp_ppr_dense(_lib.ptr(ahat.indptr), _lib.ptr(ahat.indices), _lib.ptr(ahat.val32), n,
+                                float(alpha), K, _lib.ptr(Pi), _lib.ptr(scratch), _lib.current_stream())
+    _lib.check(rc, "ppnp_ppr_dense")
+    return Pi
+
+
+def gather_gemm(Pi, H, idx=None, transpose=False, n_out=None):
+    """model.py:63 ``ppr[idx] @ H`` / model.py:65 ``ppr @ H`` in fp32 (csrc/gather_gemm.cu).
+    ``transpose=True`` gives the autograd adjoint ``ppr[idx].T @ H``."""
+    lib = _lib.load()
+    _require_cuda(Pi, H, idx)
+    if Pi.dtype != torch.float32 or H.dtype != torch.float32:
+        raise ValueError("gather_gemm is the fp32 path; use gather_gemm_bf16 for bf16 Pi")
+    if Pi.stride(1) != 1:
+        Pi = Pi.contiguous()
+    H = H.contiguous()
+    n = Pi.shape[1]
+    if idx is not None:
+        idx = idx.to(device=Pi.device, dtype=torch.int64).contiguous()
+        m = idx.numel()
+    else:
+        m = Pi.shape[0]
+    C = H.shape[1]
+    if not transpose:
+        if H.shape[0] != n:
+            raise ValueError(f"H has {H.shape[0]} rows, Pi has {n} columns")
+        out = torch.empty((m, C), dtype=torch.float32, device=Pi.device)
+    else:
+        if H.shape[0] != m:
+            raise ValueError(f"H has {H.shape[0]} rows, expected {m}")
+        out = torch.empty((n, C), dtype=torch.float32, device=Pi.device)
+    if m == 0:
+        return out.zero_()
+    with torch.cuda.device(Pi.device):
+        rc = lib.ppnp_gather_gemm_f32(_lib.ptr(Pi), Pi.stride(0), _lib.ptr(idx), m, n, _lib.ptr(H), H.stride(0), C,
+                                      _lib.ptr(out), out.stride(0), int(bool(transpose)), _lib.current_stream())
+    _lib.check(rc, "ppnp_gather_gemm_f32")
+    return out
+
+
+def to_bf16(x):
+    """fp32 -> bf16 copy (round to nearest even) through the library's own kernel."""
+    lib = _lib.load()
+    _require_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.ppnp_f32_to_bf16(_lib.ptr(x), _lib.ptr(out), x.numel(), _lib.current_stream())
+    _lib.check(rc, "ppnp_f32_to_bf16")
+    return out
+
+
+def gather_gemm_bf16(Pi_bf16, H, idx=None):
+    """The bf16 tensor-core form of model.py:63/65 (tcgen05.mma, fp32 accumulation in TMEM)."""
+    lib = _lib.load()
+    _require_cuda(Pi_bf16, H, idx)
+    if Pi_bf16.dtype != torch.bfloat16:
+        raise ValueError("Pi must be bfloat16")
+    H = H.to(torch.float32).contiguous()
+    n = Pi_bf16.shape[1]
+    if idx is not None:
+        idx = idx.to(device=Pi_bf16.device, dtype=torch.int64).contiguous()
+        m = idx.numel()
+    else:
+        m = Pi_bf16.shape[0]
+    C = H.shape[1]
+    out = torch.empty((m, C), dtype=torch.float32, device=H.device)
+    ws_bytes = lib.ppnp_gather_gemm_bf16_workspace_bytes(m, n, C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=H.device)
+    with torch.cuda.device(H.device):
+        rc = lib.ppnp_gather_gemm_bf16(_lib.ptr(Pi_bf16), Pi_bf16.stride(0), _lib.ptr(idx), m, n, _lib.ptr(H),
+                                       H.stride(0), C, _lib.ptr(out), out.stride(0), _lib.ptr(ws), ws_bytes,
+                                       _lib.current_stream())
+    _lib.check(rc, "ppnp_gather_gemm_bf16")
+    return out
+
+
+class _GatherGemmFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, H, Pi, idx):
+        ctx.Pi, ctx.idx = Pi, idx
+        return gather_gemm(Pi, H, idx)
+
+    @staticmethod
+    def backward(ctx, G):
+        return gather_gemm(ctx.Pi, G.contiguous(), ctx.idx, transpose=True), None, None
+
+
+def ppr_matmul(Pi, H, idx=None):
+    """Differentiable (w.r.t. H) ``Pi[idx] @ H``; Pi is a constant buffer as in model.py:54."""
+    return _GatherGemmFunction.apply(H, Pi, idx)
+
+
+# --------------------------------------------------------------------------- batch-main path
+def topk_thresh(ppr, k):
+    """batch-main.py:115: k-th largest of every row (== ``ppr.topk(k, -1).values[:, -1]``)."""
+    lib = _lib.load()
+    _require_cuda(ppr)
+    if ppr.stride(1) != 1:
+        ppr = ppr.contiguous()
+    n_rows, n_cols = ppr.shape
+    th = torch.empty(n_rows, dtype=torch.float32, device=ppr.device)
+    with torch.cuda.device(ppr.device):
+        rc = lib.ppnp_topk_thresh(_lib.ptr(ppr), n_rows, n_cols, ppr.stride(0), int(k), _lib.ptr(th), _lib.current_stream())
+    _lib.check(rc, "ppnp_topk_thresh")
+    return th
+
+
+def topk_sparsify_(ppr, k):
+    """batch-main.py:115-116 in place on the dense CUDA matrix (column-broadcast quirk kept)."""
+    lib = _lib.load()
+    if ppr.stride(1) != 1:
+        raise ValueError("ppr must be row-major")
+    if ppr.shape[0] != ppr.shape[1]:
+        raise ValueError("thresh[:, -1] only broadcasts against a square matrix (as in the reference)")
+    th = topk_thresh(ppr, k)
+    with torch.cuda.device(ppr.device):
+        rc = lib.ppnp_topk_mask(_lib.ptr(ppr), ppr.shape[0], ppr.shape[1], ppr.stride(0), _lib.ptr(th), _lib.current_stream())
+    _lib.check(rc, "ppnp_topk_mask")
+    return th
+
+
+@dataclass
+class SparsePPR:
+    """Compact CSR of the entries > 0 of a (sparsified) dense PPR matrix."""
+    n_rows: int
+    n_cols: int
+    indptr: torch.Tensor    # int64 [n_rows + 1]
+    indices: torch.Tensor   # int32 [nnz]
+    val: torch.Tensor       # fp32 [nnz]
+
+
+def dense_to_sparse_ppr(ppr):
+    lib = _lib.load()
+    _require_cuda(ppr)
+    if ppr.stride(1) != 1:
+        ppr = ppr.contiguous()
+    n_rows, n_cols = ppr.shape
+    row_nnz = torch.empty(n_rows, dtype=torch.int32, device=ppr.device)
+    with torch.cuda.device(ppr.device):
+        rc = lib.ppnp_dense_row_nnz(_lib.ptr(ppr), n_rows, n_cols, ppr.stride(0), _lib.ptr(row_nnz), _lib.current_stream())
+        _lib.check(rc, "ppnp_dense_row_nnz")
+        indptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=ppr.device)
+        indptr[1:] = torch.cumsum(row_nnz.to(torch.int64), 0)
+        nnz = int(indptr[-1].item())
+        indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=ppr.device)
+        val = torch.empty(max(nnz, 1), dtype=torch.float32, device=ppr.device)
+        rc = lib.ppnp_dense_to_csr(_lib.ptr(ppr), n_rows, n_cols, ppr.stride(0), _lib.ptr(indptr), _lib.ptr(indices),
+                                   _lib.ptr(val), _lib.current_stream())
+        _lib.check(rc, "ppnp_dense_to_csr")
+    return SparsePPR(n_rows, n_cols, indptr, indices[:nnz], val[:nnz])
+
+
+def batch_support(sp_ppr: SparsePPR, idx_batch):
+    """batch-main.py:140-141 on the compact matrix: bool mask ``sel`` over the n columns."""
+    lib = _lib.load()
+    idx_batch = idx_batch.to(device=sp_ppr.indices.device, dtype=torch.int64).contiguous()
+    mark = torch.zeros(sp_ppr.n_cols, dtype=torch.uint8, device=sp_ppr.indices.device)
+    if idx_batch.numel():
+        with torch.cuda.device(mark.device):
+            rc = lib.ppnp_batch_support(_lib.ptr(sp_ppr.indptr), _lib.ptr(sp_ppr.indices), _lib.ptr(idx_batch),
+                                        idx_batch.numel(), _lib.ptr(mark), _lib.current_stream())
+        _lib.check(rc, "ppnp_batch_support")
+    return mark.to(torch.bool)
+
+
+def _batch_propagate_raw(sp_ppr, idx_batch, colmap, Hsub, transpose, n_out_rows):
+    lib = _lib.load()
+    Hsub = Hsub.contiguous()
+    C = Hsub.shape[1]
+    B = idx_batch.numel()
+    if not transpose:
+        out = torch.empty((B, C), dtype=torch.float32, device=Hsub.device)
+    else:
+        out = torch.zeros((n_out_rows, C), dtype=torch.float32, device=Hsub.device)
+    if B == 0:
+        return out
+    with torch.cuda.device(Hsub.device):
+        rc = lib.ppnp_batch_propagate(_lib.ptr(sp_ppr.indptr), _lib.ptr(sp_ppr.indices), _lib.ptr(sp_ppr.val),
+                                      _lib.ptr(idx_batch), B, _lib.ptr(colmap), _lib.ptr(Hsub), Hsub.stride(0), C,
+                                      _lib.ptr(out), out.stride(0), int(bool(transpose)), _lib.current_stream())
+    _lib.check(rc, "ppnp_batch_propagate")
+    return out
+
+
+class _BatchPropagateFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Hsub, sp_ppr, idx_batch, colmap):
+        ctx.sp, ctx.idx, ctx.colmap, ctx.m = sp_ppr, idx_batch, colmap, Hsub.shape[0]
+        return _batch_propagate_raw(sp_ppr, idx_batch, colmap, Hsub, False, None)
+
+    @staticmethod
+    def backward(ctx, G):
+        return _batch_propagate_raw(ctx.sp, ctx.idx, ctx.colmap, G.contiguous(), True, ctx.m), None, None, None
+
+
+def batch_propagate(sp_ppr: SparsePPR, idx_batch, sel, Hsub):
+    """batch-main.py:142-146: ``ppr[idx_batch][:, sel] @ Hsub`` with Hsub = encoder(X[sel])
+    (differentiable w.r.t. Hsub)."""
+    dev = sp_ppr.indices.device
+    idx_batch = idx_batch.to(device=dev, dtype=torch.int64).contiguous()
+    colmap = (torch.cumsum(sel.to(torch.int32), 0, dtype=torch.int32) - 1).contiguous()
+    return _BatchPropagateFunction.apply(Hsub, sp_ppr, idx_batch, colmap)

@@ -1,0 +1,106 @@
+"""Host-side logic of the edge-stream plan (ppnp_b200/plan.py), checked on the CPU by walking
+the stream in numpy (tests/util.py walk_stream) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from util import load_golden, load_std, oracle, relerr, walk_stream
+from ppnp_b200.plan import build_stream_plan, degree_order
+
+
+def ahat_tensors(name):
+    _, adj = load_std(name)
+    ah = oracle.calc_A_hat(adj, "sym")
+    return ah, torch.from_numpy(ah.indptr.astype(np.int32)), torch.from_numpy(ah.indices.astype(np.int32)), \
+        torch.from_numpy(ah.data.astype(np.float32))
+
+
+@pytest.mark.parametrize("order", ["natural", "degree"])
+@pytest.mark.parametrize("chunk", [128, 256])
+def test_plan_invariants(order, chunk):
+    ah, ip, idx, val = ahat_tensors("cora_ml")
+    ordt = None if order == "natural" else degree_order(ip)
+    p = build_stream_plan(ip, idx, val, chunk, ordt)
+    cols = p.cols.numpy()
+    assert p.n_chunks % 32 == 0 and len(cols) == p.n_chunks * chunk
+    real = (cols & 0x7FFFFFFF) != 0x7FFFFFFF
+    assert real.sum() == ah.nnz and real[:ah.nnz].all()
+    ends = np.nonzero(cols < 0)[0]
+    assert len(ends) == p.n_segs
+    # no segment crosses a chunk boundary; chunk_seg counts the segments before each chunk
+    starts = np.concatenate([[0], ends[:-1] + 1])
+    assert (starts // chunk == ends // chunk).all()
+    cs = p.chunk_seg.numpy()
+    for c in range(p.n_chunks):
+        assert cs[c] == np.searchsorted(starts, c * chunk, side="left")
+    # partial slots are numbered in stream order and grouped by row
+    sr = p.seg_row.numpy()
+    slots = sr[sr < 0] & 0x7FFFFFFF
+    assert np.array_equal(slots, np.arange(p.n_slots))
+    fp = p.fix_ptr.numpy()
+    assert fp[0] == 0 and fp[-1] == p.n_slots and (np.diff(fp) >= 2).all()
+    finals = sr[sr >= 0]
+    assert len(set(finals.tolist()) | set(p.fix_row.numpy().tolist())) == p.n
+    # split rows are exactly the rows longer than the room left in their chunk
+    deg = np.diff(ah.indptr)
+    assert (p.fix_deg.numpy() == deg[p.fix_row.numpy()]).all()
+
+
+@pytest.mark.parametrize("name", ["cora_ml", "citeseer"])
+@pytest.mark.parametrize("order", ["natural", "degree"])
+def test_stream_walk_matches_oracle_one_step(name, order):
+    ah, ip, idx, val = ahat_tensors(name)
+    g = load_golden(name)
+    H = g["H"].astype(np.float64)
+    ordt = None if order == "natural" else degree_order(ip)
+    p = build_stream_plan(ip, idx, val, 128, ordt)
+    ref = oracle.appnp(ah, H, 0.1, 1)
+    got = walk_stream(p, H, H, 0.1, epi=0, use_vals=True)
+    assert relerr(got, ref) < 1e-7   # fp32 stored values
+
+
+def test_value_free_y_space_equals_stored_values():
+    """K steps: Z2Y (stored values) -> Y ... -> Y2Z (value-free) must equal the plain iteration."""
+    ah, ip, idx, val = ahat_tensors("citeseer")
+    g = load_golden("citeseer")
+    H = g["H"].astype(np.float64)
+    p = build_stream_plan(ip, idx, val, 128, None)
+    K, alpha = 4, 0.1
+    Z = walk_stream(p, H, H, alpha, epi=1, use_vals=True)
+    for k in range(2, K):
+        Z = walk_stream(p, Z, H, alpha, epi=2, use_vals=False)
+    Z = walk_stream(p, Z, H, alpha, epi=3, use_vals=False)
+    assert relerr(Z, oracle.appnp(ah, H, alpha, K)) < 1e-7
+
+
+def test_rw_mode_value_free():
+    _, adj = load_std("citeseer")
+    ah = oracle.calc_A_hat(adj, "rw")
+    ip = torch.from_numpy(ah.indptr.astype(np.int32))
+    idx = torch.from_numpy(ah.indices.astype(np.int32))
+    H = np.random.RandomState(0).randn(adj.shape[0], 3)
+    p = build_stream_plan(ip, idx, None, 128, None)
+    got = walk_stream(p, H, H, 0.2, epi=4, use_vals=False)
+    assert relerr(got, oracle.appnp(ah, H, 0.2, 1)) < 1e-12
+
+
+def test_hub_row_is_split_and_summed_in_order():
+    # a star: row 0 has 1000 neighbours -> many partial segments
+    import scipy.sparse as sp
+    n = 1001
+    rows = np.concatenate([np.zeros(1000, dtype=int), np.arange(1, n)])
+    cols = np.concatenate([np.arange(1, n), np.zeros(1000, dtype=int)])
+    adj = sp.csr_matrix((np.ones(2000, dtype=np.float32), (rows, cols)), shape=(n, n))
+    ah = oracle.calc_A_hat(adj, "sym")
+    p = build_stream_plan(torch.from_numpy(ah.indptr.astype(np.int32)), torch.from_numpy(ah.indices.astype(np.int32)),
+                          torch.from_numpy(ah.data.astype(np.float32)), 128, None)
+    assert p.n_fix >= 1 and 0 in p.fix_row.tolist() and p.n_slots >= 8
+    H = np.random.RandomState(1).randn(n, 5)
+    assert relerr(walk_stream(p, H, H, 0.1, 0, True), oracle.appnp(ah, H, 0.1, 1)) < 1e-7
+
+
+def test_rejects_rows_without_self_loop():
+    ip = torch.tensor([0, 1, 1], dtype=torch.int32)
+    idx = torch.tensor([0], dtype=torch.int32)
+    with pytest.raises(ValueError):
+        build_stream_plan(ip, idx, None, 128, None)

