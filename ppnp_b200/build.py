@@ -21,12 +21,27 @@ def _nvcc():
     return cand
 
 
+def source_hash(paths):
+    """Content hash of the build inputs: mtimes do not survive the copy to the GPU box."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(os.path.basename(p).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _deps(sources):
+    return sources + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(_HERE, "..", "include", "*.h"))
+
+
 def _stale(sources):
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(OUT + ".srchash"):
         return True
-    t = os.path.getmtime(OUT)
-    deps = sources + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(_HERE, "..", "include", "*.h"))
-    return any(os.path.getmtime(s) > t for s in deps)
+    with open(OUT + ".srchash") as f:
+        return f.read().strip() != source_hash(_deps(sources))
 
 
 def build_library(force=False, verbose=False):
@@ -56,6 +71,8 @@ def build_library(force=False, verbose=False):
         raise RuntimeError(f"link failed:\n{r.stdout}")
     with open(os.path.join(objdir, "build.log"), "w") as f:
         f.write("\n".join(log))
+    with open(OUT + ".srchash", "w") as f:
+        f.write(source_hash(_deps(sources)))
     if verbose:
         print("\n".join(log))
     return OUT
