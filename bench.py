@@ -56,7 +56,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
             "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
             "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -91,10 +91,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._halt.wait(0.05)
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,

@@ -41,7 +41,6 @@ extern "C" {
 
 /* bit 31 of a stream column: last edge of its segment; of a seg_row entry: partial segment */
 #define PPNP_FLAG 0x80000000u
-#define PPNP_NULL_COL 0x7fffffff /* padding edge: contributes nothing */
 
 const char* ppnp_last_error(void);
 int ppnp_version(void);
@@ -76,7 +75,7 @@ int ppnp_csr_normalize(const int32_t* indptr, const int32_t* indices, const floa
  * The adjacency is consumed as an "edge stream" (ppnp_b200/plan.py builds it from the
  * normalised CSR): the rows of A_hat in processing order, cut into segments that never cross
  * a chunk of `chunk_edges` edges.  cols[e] = column | PPNP_FLAG on the last edge of a
- * segment, PPNP_NULL_COL for padding; seg_row[s] = row the segment finishes, or
+ * segment (padding after the last segment: column 0, no flag, never emitted); seg_row[s] = row the segment finishes, or
  * PPNP_FLAG | slot when the row is split over several segments (the partial sums go to
  * partial[slot] and ppnp_spmm_fixup adds them up in slot order -- deterministic);
  * chunk_seg[c] = index of the first segment of chunk c.  vals (nullable) are the stored

@@ -8,13 +8,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppnp_b200.so")
+# PPNP_B200_LIB selects an experimental build of the same sources (tools/build_variants.py)
+LIB_PATH = os.environ.get("PPNP_B200_LIB") or os.path.join(_HERE, "libppnp_b200.so")
 
 # epilogues / modes (keep in sync with include/ppnp_b200.h)
 MODE_SYM, MODE_RW = 0, 1
 EPI_PLAIN, EPI_Z2Y, EPI_Y, EPI_Y2Z, EPI_RW = 0, 1, 2, 3, 4
 FLAG = 0x80000000
-NULL_COL = 0x7FFFFFFF
 
 
 class PlanStruct(C.Structure):

@@ -44,20 +44,31 @@ def _stale(sources):
         return f.read().strip() != source_hash(_deps(sources))
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (e.g. defines=['PPNP_SPMM_U4=8'], out='libvariant.so')
+    that ppnp_b200._lib loads when PPNP_B200_LIB points at it."""
+    if out is not None:
+        return _build(sorted(glob.glob(os.path.join(CSRC, '*.cu'))), list(defines), out, verbose, tag=os.path.basename(out))
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     if not sources:
         raise RuntimeError("no CUDA sources found")
     if not force and not _stale(sources):
         return OUT
-    objdir = os.path.join(_HERE, "csrc", "_obj")
+    _build(sources, [], OUT, verbose, tag="")
+    with open(OUT + ".srchash", "w") as f:
+        f.write(source_hash(_deps(sources)))
+    return OUT
+
+
+def _build(sources, defines, out_path, verbose, tag):
+    objdir = os.path.join(_HERE, "csrc", "_obj" + ("_" + tag if tag else ""))
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     objs, procs = [], []
     for s in sources:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", s, "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:
@@ -65,17 +76,15 @@ def build_library(force=False, verbose=False):
         log.append(f"== {os.path.basename(s)}\n{out}")
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}:\n{out}")
-    cmd = [nvcc, "-shared", "-o", OUT, *objs, "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", out_path, *objs, "-lcuda"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     with open(os.path.join(objdir, "build.log"), "w") as f:
         f.write("\n".join(log))
-    with open(OUT + ".srchash", "w") as f:
-        f.write(source_hash(_deps(sources)))
     if verbose:
         print("\n".join(log))
-    return OUT
+    return out_path
 
 
 if __name__ == "__main__":

@@ -21,127 +21,143 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-template <int G>
-struct GroupCfg {
-    // indices loaded per lane and batch: keep the per-group request >= 64 B (two full sectors)
-    static constexpr int IPL = (G >= 16) ? 1 : (G == 8 ? 2 : 4);
-    static constexpr int EB = G * IPL;  // edges per batch
-};
+// tuning knobs (overridable at build time for experiments, see tools/)
+#ifndef PPNP_SPMM_MINBLOCKS
+#define PPNP_SPMM_MINBLOCKS 4   // resident 256-thread CTAs per SM the register budget is capped for
+#endif
+#ifndef PPNP_SPMM_U4
+#define PPNP_SPMM_U4 4          // float4 gathers issued back to back per group (VEC == 4)
+#endif
 
-template <int IPL>
-struct IdxLoad;
-template <>
-struct IdxLoad<1> {
-    __device__ __forceinline__ static void load(const int32_t* p, int (&r)[1]) { r[0] = __ldcs(p); }
-    __device__ __forceinline__ static void loadf(const float* p, float (&r)[1]) { r[0] = __ldcs(p); }
-};
-template <>
-struct IdxLoad<2> {
-    __device__ __forceinline__ static void load(const int32_t* p, int (&r)[2]) {
-        const int2 v = __ldcs(reinterpret_cast<const int2*>(p)); r[0] = v.x; r[1] = v.y;
+// Finish a segment: either park the partial sum or apply the epilogue and stream the row out.
+// Kept out of line so that the (rarely taken, per segment end) code exists once in the kernel.
+template <int VEC>
+__device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t, int sv, float deg, bool active,
+                                          float* __restrict__ Zout, float* __restrict__ partial, int ld, int f,
+                                          float alpha, int epi) {
+    if (!active) return;
+    if (sv < 0) {
+        acc.store(partial + (int64_t)(sv & 0x7fffffff) * ld + f);
+    } else {
+        float a, bb;
+        epi_coef(epi, alpha, deg, a, bb);
+        Vec<VEC>::axpby(a, acc, bb, t).store_stream(Zout + (int64_t)sv * ld + f);
     }
-    __device__ __forceinline__ static void loadf(const float* p, float (&r)[2]) {
-        const float2 v = __ldcs(reinterpret_cast<const float2*>(p)); r[0] = v.x; r[1] = v.y;
-    }
-};
-template <>
-struct IdxLoad<4> {
-    __device__ __forceinline__ static void load(const int32_t* p, int (&r)[4]) {
-        const int4 v = __ldcs(reinterpret_cast<const int4*>(p)); r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-    }
-    __device__ __forceinline__ static void loadf(const float* p, float (&r)[4]) {
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(p)); r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-    }
-};
+}
 
-template <int VEC, int G, bool HAS_VAL, int U>
-__global__ void __launch_bounds__(256)
+// A slab is G consecutive edges of the chunk, one column index per lane of the group.  Slabs are
+// software-pipelined three deep: indices of slab j+2 in flight, segment rows of slab j+1 in
+// flight, gathers of slab j being issued.
+template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE>
+__global__ void __launch_bounds__(256, PPNP_SPMM_MINBLOCKS)
 spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
                    const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
                    int64_t n_chunks, int chunk_edges,
                    const float* __restrict__ Zin, const float* __restrict__ T,
                    float* __restrict__ Zout, float* __restrict__ partial,
-                   int64_t ld, int F, float alpha, int epi) {
+                   int ld, int F, float alpha, int epi) {
     using V = Vec<VEC>;
-    constexpr int IPL = GroupCfg<G>::IPL;
-    constexpr int EB = GroupCfg<G>::EB;
-    constexpr int GPW = 32 / G;  // groups per warp
-    static_assert(EB % U == 0, "sub-batch must divide the batch");
+    constexpr int GPW = 32 / G;      // groups per warp
+    static_assert(G % U == 0, "sub-batch must divide the slab");
 
     const int lane = threadIdx.x & 31;
     const int g = lane / G;
     const int lg = lane % G;
-    const unsigned gshift = (unsigned)(g * G);
-    const unsigned gmask = (G == 32) ? FULL : ((1u << G) - 1u);
-    const unsigned lt = (1u << lg) - 1u;  // lower lanes of my group
+    // The groups of a warp run in lock step (same trip counts everywhere), so shuffles and ballots
+    // use the full mask; the only group-divergent code is the per-segment emit, which has none.
+    const int gshift = g * G;
+    const unsigned gbits = (G == 32) ? FULL : ((1u << G) - 1u);
+    const unsigned lt = (1u << lg) - 1u;  // lower lanes of my group (after shifting the ballot down)
 
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t total_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * GPW;
 
     const int f = ((int)blockIdx.y * G + lg) * VEC;
-    const bool active = f < F;
+    const bool active = FULL_TILE ? true : (f < F);   // FULL_TILE: F == gridDim.y * G * VEC, no idle lanes
+    // row addresses as base + col * row_bytes: one IMAD.WIDE.U32 per gathered row
+    const char* zbase = reinterpret_cast<const char*>(Zin + f);
+    const char* tbase = reinterpret_cast<const char*>(T + f);
+    const unsigned row_bytes = (unsigned)ld * 4u;
+    const int n_slabs = chunk_edges / G;
 
     for (int64_t c = warp_global * GPW + g; c < n_chunks; c += total_groups) {
         int s = __ldg(chunk_seg + c);
-        const int64_t ebase = c * (int64_t)chunk_edges;
+        const int32_t* cp = cols + c * (int64_t)chunk_edges + lg;
+        const float* vp = HAS_VAL ? vals + c * (int64_t)chunk_edges + lg : nullptr;
         V acc; acc.zero();
-        float cnt = 0.f;
+        int seg_begin = 0;  // chunk-local position where the running segment started
 
-        for (int b = 0; b < chunk_edges; b += EB) {
-            int raw[IPL];
-            float w[IPL];
-            IdxLoad<IPL>::load(cols + ebase + b + lg * IPL, raw);
-            if (HAS_VAL) IdxLoad<IPL>::loadf(vals + ebase + b + lg * IPL, w);
+        // pipeline prologue: slab 0 -> stage 1 (indices known, segment rows requested), slab 1 -> stage 2
+        int raw1 = __ldcs(cp);
+        float w1 = HAS_VAL ? __ldcs(vp) : 0.f;
+        int raw2 = __ldcs(cp + G);
+        float w2 = HAS_VAL ? __ldcs(vp + G) : 0.f;
+        unsigned ends1 = (__ballot_sync(FULL, raw1 < 0) >> gshift) & gbits;
+        int segv1 = 0;
+        if (raw1 < 0) segv1 = __ldcs(seg_row + s + __popc(ends1 & lt));
+        s += __popc(ends1);
 
-            // position of every segment end of this batch in seg_row (edge order: lane-major)
-            int pre = 0, tot = 0;
-#pragma unroll
-            for (int k = 0; k < IPL; ++k) {
-                const unsigned m = (__ballot_sync(FULL, raw[k] < 0) >> gshift) & gmask;
-                pre += __popc(m & lt);
-                tot += __popc(m);
+#pragma unroll 1
+        for (int j = 0; j < n_slabs; ++j) {
+            const int raw0 = raw1;
+            const float w0 = w1;
+            const unsigned ends0 = ends1;
+            const int segv0 = segv1;
+            // stage 1 <- stage 2
+            raw1 = raw2;
+            w1 = w2;
+            ends1 = (__ballot_sync(FULL, raw1 < 0) >> gshift) & gbits;
+            segv1 = 0;
+            if (raw1 < 0) segv1 = __ldcs(seg_row + s + __popc(ends1 & lt));
+            s += __popc(ends1);
+            // stage 2 <- memory
+            raw2 = 0;
+            if (j + 2 < n_slabs) {
+                raw2 = __ldcs(cp + (j + 2) * G);
+                if (HAS_VAL) w2 = __ldcs(vp + (j + 2) * G);
             }
-            int segv[IPL];
-#pragma unroll
-            for (int k = 0; k < IPL; ++k) {
-                segv[k] = 0;
-                if (raw[k] < 0) { segv[k] = __ldcs(seg_row + s + pre); ++pre; }
-            }
-            s += tot;
 
 #pragma unroll
-            for (int u0 = 0; u0 < EB; u0 += U) {
-                V v[U], t[U];
-                int ru[U], sv[U];
-                float wu[U];
+            for (int u0 = 0; u0 < G; u0 += U) {
+                const unsigned sub = (ends0 >> u0) & ((1u << U) - 1u);
+                if (!__any_sync(FULL, sub != 0)) {   // warp-uniform: no group of this warp ends a segment here
+                    // ---- fast path: no segment ends among these U edges
+                    V v[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int e = u0 + u;
-                    ru[u] = __shfl_sync(FULL, raw[e % IPL], e / IPL, G);
-                    sv[u] = __shfl_sync(FULL, segv[e % IPL], e / IPL, G);
-                    if (HAS_VAL) wu[u] = __shfl_sync(FULL, w[e % IPL], e / IPL, G);
-                    const int col = ru[u] & 0x7fffffff;
-                    v[u].zero();
-                    t[u].zero();
-                    if (active && col != PPNP_NULL_COL) v[u] = V::load(Zin + (int64_t)col * ld + f);
-                    if (active && ru[u] < 0 && sv[u] >= 0) t[u] = V::load_stream(T + (int64_t)sv[u] * ld + f);
-                }
+                    for (int u = 0; u < U; ++u) {
+                        const int col = __shfl_sync(FULL, raw0, u0 + u, G);
+                        v[u].zero();
+                        if (active) v[u] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                    }
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (HAS_VAL) acc.fma(wu[u], v[u]); else acc.add(v[u]);
-                    cnt += ((ru[u] & 0x7fffffff) != PPNP_NULL_COL) ? 1.f : 0.f;
-                    if (ru[u] < 0) {
-                        if (sv[u] < 0) {
-                            const int64_t slot = sv[u] & 0x7fffffff;
-                            if (active) acc.store(partial + slot * ld + f);
-                        } else {
-                            float a, bb;
-                            epi_coef(epi, alpha, cnt, a, bb);
-                            const V o = V::axpby(a, acc, bb, t[u]);
-                            if (active) o.store_stream(Zout + (int64_t)sv[u] * ld + f);
+                    for (int u = 0; u < U; ++u) {
+                        if (HAS_VAL) acc.fma(__shfl_sync(FULL, w0, u0 + u, G), v[u]); else acc.add(v[u]);
+                    }
+                } else {
+                    // ---- general path: some of these edges finish a segment
+                    V v[U], t[U];
+                    int ru[U], sv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        ru[u] = __shfl_sync(FULL, raw0, u0 + u, G);
+                        sv[u] = __shfl_sync(FULL, segv0, u0 + u, G);
+                        v[u].zero();
+                        t[u].zero();
+                        if (active) v[u] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)(ru[u] & 0x7fffffff) * row_bytes));
+                        if (active && ru[u] < 0 && sv[u] >= 0) t[u] = V::load_stream(reinterpret_cast<const float*>(tbase + (uint64_t)(unsigned)sv[u] * row_bytes));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (HAS_VAL) acc.fma(__shfl_sync(FULL, w0, u0 + u, G), v[u]); else acc.add(v[u]);
+                        if (ru[u] < 0) {
+                            const int pos = j * G + u0 + u;
+                            {   // copies: the out-of-line call takes references, acc itself must stay in registers
+                                const V a2 = acc, t2 = t[u];
+                                emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi);
+                            }
+                            acc.zero();
+                            seg_begin = pos + 1;
                         }
-                        acc.zero();
-                        cnt = 0.f;
                     }
                 }
             }
@@ -200,28 +216,25 @@ template <int VEC, int G>
 int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Zout, float* partial,
                 int64_t ld, int F, float alpha, int epi, bool use_vals, cudaStream_t stream) {
     constexpr int THREADS = 256;
-    constexpr int U = (VEC == 4) ? 4 : ((GroupCfg<G>::EB >= 8) ? 8 : GroupCfg<G>::EB);
+    constexpr int U = (VEC == 4) ? ((G >= PPNP_SPMM_U4) ? PPNP_SPMM_U4 : G) : ((G >= 8) ? 8 : G);
     constexpr int GPW = 32 / G;
     const int tiles = (F + G * VEC - 1) / (G * VEC);
     const int64_t groups_per_block = (THREADS / 32) * GPW;
     const int64_t need = (p->n_chunks + groups_per_block - 1) / groups_per_block;
-    if (use_vals) {
-        auto k = spmm_stream_kernel<VEC, G, true, U>;
-        static thread_local int occ = 0;
-        if (!occ) occ = blocks_per_sm(k, THREADS);
-        const int64_t cap = (int64_t)sm_count() * occ;
-        dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)tiles);
-        k<<<grid, THREADS, 0, stream>>>(p->cols, p->vals, p->seg_row, p->chunk_seg, p->n_chunks, p->chunk_edges,
-                                        Zin, T, Zout, partial, ld, F, alpha, epi);
-    } else {
-        auto k = spmm_stream_kernel<VEC, G, false, U>;
-        static thread_local int occ = 0;
-        if (!occ) occ = blocks_per_sm(k, THREADS);
-        const int64_t cap = (int64_t)sm_count() * occ;
-        dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)tiles);
-        k<<<grid, THREADS, 0, stream>>>(p->cols, nullptr, p->seg_row, p->chunk_seg, p->n_chunks, p->chunk_edges,
-                                        Zin, T, Zout, partial, ld, F, alpha, epi);
-    }
+    const bool full_tile = (tiles * G * VEC == F);
+#define PPNP_LAUNCH(HV_, FT_)                                                                                      \
+    do {                                                                                                           \
+        auto k = spmm_stream_kernel<VEC, G, HV_, U, FT_>;                                                          \
+        static thread_local int occ = 0;                                                                           \
+        if (!occ) occ = blocks_per_sm(k, THREADS);                                                                 \
+        const int64_t cap = (int64_t)sm_count() * occ;                                                             \
+        dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)tiles);                                           \
+        k<<<grid, THREADS, 0, stream>>>(p->cols, HV_ ? p->vals : nullptr, p->seg_row, p->chunk_seg, p->n_chunks,   \
+                                        p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi);            \
+    } while (0)
+    if (use_vals) { if (full_tile) PPNP_LAUNCH(true, true); else PPNP_LAUNCH(true, false); }
+    else          { if (full_tile) PPNP_LAUNCH(false, true); else PPNP_LAUNCH(false, false); }
+#undef PPNP_LAUNCH
     PPNP_CHECK_LAUNCH("spmm_stream_kernel");
     if (p->n_fix > 0) {
         const int64_t needf = (p->n_fix + groups_per_block - 1) / groups_per_block;
@@ -287,7 +300,7 @@ int ppnp_spmm_step(const ppnp_plan_t* plan, const float* Zin, const float* T, fl
     if (rc) return rc;
     PPNP_REQUIRE(Zin && T && Zout, "null matrix pointer");
     PPNP_REQUIRE(Zin != Zout, "Zout must not alias Zin");
-    PPNP_REQUIRE(F > 0 && ld >= F, "need 0 < F <= ld");
+    PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
     PPNP_REQUIRE(epi >= PPNP_EPI_PLAIN && epi <= PPNP_EPI_RW, "bad epilogue");
@@ -302,7 +315,7 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
     if (rc) return rc;
     PPNP_REQUIRE(H && Z && scratch, "null matrix pointer");
     PPNP_REQUIRE(H != Z && H != scratch && Z != scratch, "H, Z, scratch must be distinct buffers");
-    PPNP_REQUIRE(F > 0 && ld >= F, "need 0 < F <= ld");
+    PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(K >= 1, "K >= 1");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     PPNP_REQUIRE(mode == PPNP_MODE_SYM || mode == PPNP_MODE_RW, "bad mode");

@@ -240,6 +240,21 @@ def to_bf16(x):
     return out
 
 
+def to_bf16_padded(Pi):
+    """bf16 shadow of a dense fp32 matrix with the row stride padded to a multiple of 64 elements
+    (16-byte aligned rows, whole k-blocks): what ``gather_gemm_bf16`` consumes.  Returns the
+    n_rows x n_cols view into the padded buffer."""
+    n_rows, n_cols = Pi.shape
+    ld = ((n_cols + 63) // 64) * 64
+    buf = torch.zeros((n_rows, ld), dtype=torch.bfloat16, device=Pi.device)
+    # convert in row slabs of <= 256 MB so the fp32 source never needs a second full-size copy
+    rows_per = max(1, (64 << 20) // max(n_cols, 1))
+    for r0 in range(0, n_rows, rows_per):
+        r1 = min(n_rows, r0 + rows_per)
+        buf[r0:r1, :n_cols] = to_bf16(Pi[r0:r1])
+    return buf[:, :n_cols]
+
+
 def gather_gemm_bf16(Pi_bf16, H, idx=None):
     """The bf16 tensor-core form of model.py:63/65 (tcgen05.mma, fp32 accumulation in TMEM)."""
     lib = _lib.load()

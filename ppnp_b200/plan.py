@@ -19,7 +19,6 @@ import torch
 from . import _lib
 
 FLAG_I32 = -(1 << 31)          # PPNP_FLAG as a signed int32
-NULL_COL = _lib.NULL_COL
 
 
 @dataclass
@@ -145,7 +144,8 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None):
     n_chunks = (nnz + W - 1) // W
     n_chunks = ((n_chunks + 31) // 32) * 32
     total = n_chunks * W
-    cols = torch.full((total,), NULL_COL, dtype=torch.int32, device=dev)
+    # padding edges (after the last segment end) point at row 0 and are never emitted
+    cols = torch.zeros(total, dtype=torch.int32, device=dev)
     cols[:nnz] = stream_cols
     cols[seg_end] |= FLAG_I32
     svals = None

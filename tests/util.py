@@ -62,9 +62,8 @@ def walk_stream(plan, Zin, T, alpha, epi, use_vals):
         for e in range(c * W, (c + 1) * W):
             raw = int(cols[e])
             col = raw & 0x7FFFFFFF
-            if col != 0x7FFFFFFF:
-                acc += (vals[e] if use_vals else 1.0) * Zin[col]
-                cnt += 1
+            acc += (vals[e] if use_vals else 1.0) * Zin[col]
+            cnt += 1
             if raw < 0:
                 sv = int(seg_row[s])
                 s += 1
@@ -76,7 +75,6 @@ def walk_stream(plan, Zin, T, alpha, epi, use_vals):
                     written[sv] += 1
                 acc = np.zeros(F)
                 cnt = 0
-        assert cnt == 0 or c == plan.n_chunks - 1 or True
     fp = plan.fix_ptr.cpu().numpy()
     fr = plan.fix_row.cpu().numpy()
     fd = plan.fix_deg.cpu().numpy()
