@@ -37,6 +37,7 @@ WORKLOADS = {
     "rmat2m": (2_000_000, 26_400_000, 21, 64),
     "rmat100m": (100_000_000, 1_120_000_000, 27, 16),
     "rmat16m": (16_000_000, 220_000_000, 24, 16),
+    "rmatl2": (250_000, 13_200_000, 18, 64),     # same recipe, Z (64 MB) fits the L2: gather-rate probe
     "tiny": (20_000, 300_000, 15, 64),
 }
 
@@ -337,7 +338,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--order", default="natural", choices=["natural", "degree"])
+    ap.add_argument("--order", default="degree", choices=["natural", "degree"])
     ap.add_argument("--chunk-edges", type=int, default=256)
     ap.add_argument("--use-vals", action="store_true", help="stored-value form in every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -93,7 +93,7 @@ typedef struct ppnp_plan {
     int32_t reserved;
     const int32_t* cols;      /* [n_edges]                                              */
     const float* vals;        /* [n_edges] or NULL                                      */
-    const int32_t* seg_row;   /* [n_segs]                                               */
+    const int32_t* seg_row;   /* [n_segs + 64] (64 readable spare entries after the last one) */
     const int32_t* chunk_seg; /* [n_chunks]                                             */
     const int32_t* fix_ptr;   /* [n_fix + 1] slot ranges                                */
     const int32_t* fix_row;   /* [n_fix]                                                */

@@ -93,8 +93,9 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
         int raw2 = __ldcs(cp + G);
         float w2 = HAS_VAL ? __ldcs(vp + G) : 0.f;
         unsigned ends1 = (__ballot_sync(FULL, raw1 < 0) >> gshift) & gbits;
-        int segv1 = 0;
-        if (raw1 < 0) segv1 = __ldcs(seg_row + s + __popc(ends1 & lt));
+        // unconditional (seg_row is padded): no predicated merge, so nothing waits on this load
+        // until the slab that needs it is processed
+        int segv1 = __ldcs(seg_row + s + __popc(ends1 & lt));
         s += __popc(ends1);
 
 #pragma unroll 1
@@ -107,14 +108,14 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
             raw1 = raw2;
             w1 = w2;
             ends1 = (__ballot_sync(FULL, raw1 < 0) >> gshift) & gbits;
-            segv1 = 0;
-            if (raw1 < 0) segv1 = __ldcs(seg_row + s + __popc(ends1 & lt));
+            if (j + 1 >= n_slabs) ends1 = 0;   // past the chunk: the replayed slab is never processed
+            segv1 = __ldcs(seg_row + s + __popc(ends1 & lt));
             s += __popc(ends1);
-            // stage 2 <- memory
-            raw2 = 0;
-            if (j + 2 < n_slabs) {
-                raw2 = __ldcs(cp + (j + 2) * G);
-                if (HAS_VAL) w2 = __ldcs(vp + (j + 2) * G);
+            // stage 2 <- memory (clamped to the last slab of the chunk: always a valid address)
+            {
+                const int jn = (j + 2 < n_slabs) ? j + 2 : n_slabs - 1;
+                raw2 = __ldcs(cp + jn * G);
+                if (HAS_VAL) w2 = __ldcs(vp + jn * G);
             }
 
 #pragma unroll

@@ -36,11 +36,12 @@ class StreamPlan:
     fix_deg: torch.Tensor       # fp32 [n_fix]
     n_slots: int
     order: Optional[torch.Tensor] = None   # processing order of the rows (None = natural)
+    n_segs_real: int = 0
     _struct: object = field(default=None, repr=False)
 
     @property
     def n_segs(self):
-        return int(self.seg_row.numel())
+        return self.n_segs_real if self.n_segs_real else int(self.seg_row.numel())
 
     @property
     def n_fix(self):
@@ -76,7 +77,7 @@ class StreamPlan:
         mv = lambda t: None if t is None else t.to(device)
         return StreamPlan(self.n, self.nnz, self.chunk_edges, self.n_chunks, mv(self.cols), mv(self.vals),
                           mv(self.seg_row), mv(self.chunk_seg), mv(self.fix_ptr), mv(self.fix_row),
-                          mv(self.fix_deg), self.n_slots, mv(self.order))
+                          mv(self.fix_deg), self.n_slots, mv(self.order), self.n_segs_real)
 
 
 def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None):
@@ -140,6 +141,9 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None):
     slot = torch.cumsum(seg_partial.to(torch.int64), 0) - 1
     n_slots = int(seg_partial.sum().item())
     seg_row = torch.where(seg_partial, slot + FLAG_I32, owner_row).to(torch.int32)
+    # 64 spare entries: the kernel prefetches seg_row[s + lane] without a bounds check
+    seg_row = torch.cat([seg_row, torch.zeros(64, dtype=torch.int32, device=dev)])
+    n_real_segs = n_segs
 
     n_chunks = (nnz + W - 1) // W
     n_chunks = ((n_chunks + 31) // 32) * 32
@@ -163,7 +167,7 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None):
     fix_deg = L[fix_rows_pos].to(torch.float32)
     return StreamPlan(n=n, nnz=nnz, chunk_edges=W, n_chunks=n_chunks, cols=cols, vals=svals, seg_row=seg_row,
                       chunk_seg=chunk_seg, fix_ptr=fp.to(torch.int32), fix_row=fix_row, fix_deg=fix_deg,
-                      n_slots=n_slots, order=order)
+                      n_slots=n_slots, order=order, n_segs_real=n_real_segs)
 
 
 def degree_order(indptr):
