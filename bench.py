@@ -35,7 +35,7 @@ ALPHA, KSTEPS = 0.1, 10
 WORKLOADS = {
     #            n            raw draws      scale  F
     "rmat2m": (2_000_000, 26_400_000, 21, 64),
-    "rmat100m": (100_000_000, 1_120_000_000, 27, 16),
+    "rmat100m": (100_000_000, 1_050_000_000, 27, 16),
     "rmat16m": (16_000_000, 220_000_000, 24, 16),
     "rmatl2": (250_000, 13_200_000, 18, 64),     # same recipe, Z (64 MB) fits the L2: gather-rate probe
     "tiny": (20_000, 300_000, 15, 64),

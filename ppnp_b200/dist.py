@@ -1,0 +1,398 @@
+"""Row-partitioned multi-GPU APPNP (BASELINE.json config 5; not in the reference, which is
+single-process -- SURVEY.md section 2.3 / 8e).
+
+Rank p owns a contiguous block of rows of A_hat, Z and H.  Row i of Z_{k+1} needs the Z_k rows of
+i's neighbours only, so one exchange per iteration suffices:
+
+  * the shard's column ids are remapped to [local rows | halo slots]; halo slots are the distinct
+    remote rows the shard references, grouped by owner and sorted, so the NCCL all-to-all receives
+    straight into the tail of the Z buffer (no unpack);
+  * every step: pack the rows each peer needs (send lists exchanged once at set-up), all_to_all
+    over NVLink, then the same fused SpMM+teleport kernel as on one GPU (csrc/appnp_spmm.cu) over
+    the extended buffer;
+  * rows whose neighbours are all local ("interior") do not depend on the exchange: they are a
+    separate edge stream that runs on the compute stream while the all-to-all is in flight, the
+    boundary rows follow once the halo has landed;
+  * row-block boundaries are chosen by the non-zero prefix sum, not by row count (R-MAT rows are
+    heavily skewed: equal row blocks would put 44 % of the edges on rank 0 of 8).
+
+The backward pass is the same operator on the upstream gradient (A_hat symmetric), so it uses
+the same partition and halo lists.
+
+Everything here is index bookkeeping plus torch.distributed calls; the arithmetic is in the CUDA
+library.  ``ShardTopology`` and ``HaloExchange`` are device-agnostic so that the host logic is
+tested on CPU with the gloo backend (tests/test_dist_cpu.py).
+"""
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------ partitioning
+def balanced_row_blocks(weights, world):
+    """Boundaries lo_0=0 <= ... <= lo_world=n such that every block carries ~1/world of the weight
+    (weights = per-row non-zeros incl. the self loop).  Returns a python list of world+1 ints."""
+    w = weights.to(torch.float64)
+    prefix = torch.cumsum(w, 0)
+    total = float(prefix[-1])
+    targets = torch.arange(1, world, dtype=torch.float64, device=w.device) * (total / world)
+    cuts = torch.searchsorted(prefix, targets, right=False) + 1
+    bounds = [0] + [int(c) for c in cuts.tolist()] + [int(w.numel())]
+    for i in range(1, len(bounds)):
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+@dataclass
+class ShardTopology:
+    """Local view of rank ``rank``: remapped CSR of its rows of A + I and the halo description."""
+    rank: int
+    world: int
+    bounds: List[int]                 # world + 1 row boundaries
+    n_local: int
+    indptr: torch.Tensor              # int64 [n_local + 1]
+    indices: torch.Tensor             # int32 [nnz_local], local rows then halo slots (n_local + h)
+    halo_cols: torch.Tensor           # int64 [n_halo] global ids, grouped by owner, ascending
+    recv_counts: List[int]            # halo rows owned by each rank
+    interior: torch.Tensor            # bool [n_local]: row references no halo slot
+
+    @property
+    def n_halo(self):
+        return int(self.halo_cols.numel())
+
+
+def build_shard_topology(indptr_local, cols_global, bounds, rank):
+    """indptr_local/cols_global: CSR of this rank's rows of A + I with GLOBAL column ids (sorted)."""
+    world = len(bounds) - 1
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n_local = hi - lo
+    dev = cols_global.device
+    cg = cols_global.to(torch.int64)
+    is_local = (cg >= lo) & (cg < hi)
+    remote = cg[~is_local]
+    halo_cols = torch.unique(remote, sorted=True)          # ascending global id == grouped by owner
+    b = torch.tensor(bounds, dtype=torch.int64, device=dev)
+    owner = torch.searchsorted(b, halo_cols, right=True) - 1
+    recv_counts = torch.bincount(owner, minlength=world).tolist() if halo_cols.numel() else [0] * world
+    remap = torch.where(is_local, cg - lo, n_local + torch.searchsorted(halo_cols, cg))
+    ip = indptr_local.to(torch.int64)
+    # interior rows: every column local
+    row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), ip[1:] - ip[:-1])
+    has_remote = torch.zeros(n_local, dtype=torch.bool, device=dev)
+    has_remote[row_of[~is_local]] = True
+    return ShardTopology(rank=rank, world=world, bounds=list(bounds), n_local=n_local, indptr=ip,
+                         indices=remap.to(torch.int32), halo_cols=halo_cols, recv_counts=[int(c) for c in recv_counts],
+                         interior=~has_remote)
+
+
+# ------------------------------------------------------------------------------ halo exchange
+class HaloExchange:
+    """Per-step exchange of boundary rows.  Set-up trades the halo id lists once (all_to_all of
+    counts, then of ids); ``start``/``finish`` move the rows: pack -> all_to_all_single -> the halo
+    region of the destination buffer."""
+
+    def __init__(self, topo: ShardTopology, group=None):
+        self.topo, self.group = topo, group
+        dev = topo.halo_cols.device
+        world = topo.world
+        recv_counts = torch.tensor(topo.recv_counts, dtype=torch.int64, device=dev)
+        send_counts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(send_counts, recv_counts, group=group)          # how many rows each peer wants from me
+        self.recv_counts = topo.recv_counts
+        self.send_counts = [int(c) for c in send_counts.tolist()]
+        want = topo.halo_cols                                                   # ids I want, grouped by owner
+        give = torch.empty(sum(self.send_counts), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(give, want, output_split_sizes=self.send_counts, input_split_sizes=self.recv_counts, group=group)
+        lo = topo.bounds[topo.rank]
+        self.send_idx = (give - lo).contiguous()                                # local rows to ship, grouped by destination
+        if self.send_idx.numel():
+            assert int(self.send_idx.min()) >= 0 and int(self.send_idx.max()) < topo.n_local
+        self._send_buf = {}
+
+    def bytes_per_step(self, F):
+        return (sum(self.send_counts) + sum(self.recv_counts)) * F * 4
+
+    def exchange(self, Zext, async_op=False):
+        """Fill rows n_local.. of ``Zext`` ([n_local + n_halo, F]) with the owners' current rows 0..n_local-1."""
+        t = self.topo
+        F = Zext.shape[1]
+        key = (F, Zext.device)
+        buf = self._send_buf.get(key)
+        if buf is None:
+            buf = torch.empty((max(self.send_idx.numel(), 1), F), dtype=Zext.dtype, device=Zext.device)
+            self._send_buf[key] = buf
+        send = buf[: self.send_idx.numel()]
+        if self.send_idx.numel():
+            torch.index_select(Zext[: t.n_local], 0, self.send_idx, out=send)
+        recv = Zext[t.n_local:]
+        return dist.all_to_all_single(recv, send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
+                                      group=self.group, async_op=async_op)
+
+
+# ------------------------------------------------------------------------------ GPU propagation
+class PartitionedPropagation:
+    """K-step APPNP over the shard (CUDA).  Two edge streams: interior rows (overlap the exchange) and
+    boundary rows (after it)."""
+
+    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, overlap=True, group=None,
+                 step_fn=None):
+        """``step_fn(plan, Zin, T, Zout, alpha, epi, use_vals)`` replaces the CUDA launch; it exists so
+        that tests can drive this orchestration on CPU tensors (gloo) with a numpy walker of the
+        plan.  The package itself ships no CPU implementation: the default is the CUDA library."""
+        self.topo = topo
+        self._step_fn = step_fn
+        self.overlap = overlap
+        self.exchange = HaloExchange(topo, group)
+        dev = topo.indices.device
+        ip = topo.indptr
+        deg = (ip[1:] - ip[:-1])
+        lo = topo.bounds[topo.rank]
+        # stored values of the first step: dinv_i * dinv_j with GLOBAL degrees
+        dinv_ext = torch.cat([deg_global_dinv[lo: lo + topo.n_local], deg_global_dinv[topo.halo_cols]])
+        row_of = torch.repeat_interleave(torch.arange(topo.n_local, device=dev), deg)
+        vals = dinv_ext[row_of] * dinv_ext[topo.indices.to(torch.int64)]
+        del row_of
+        order_int = torch.nonzero(topo.interior).flatten()
+        order_bnd = torch.nonzero(~topo.interior).flatten()
+        self.plans = []
+        for rows in ((order_int, order_bnd) if overlap else (torch.arange(topo.n_local, device=dev),)):
+            if rows.numel() == 0:
+                self.plans.append(None)
+                continue
+            d = deg[rows]
+            order = rows[torch.sort(d, descending=True, stable=True).indices]
+            self.plans.append(_SubGraph(build_stream_plan_subset(ip, topo.indices, vals, chunk_edges, order, topo.n_local), step_fn))
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+
+    def n_ext(self):
+        return self.topo.n_local + self.topo.n_halo
+
+    def propagate(self, H_ext, Z_ext, S_ext, K, alpha):
+        """H_ext/Z_ext/S_ext: [n_local + n_halo, F] buffers; H_ext[:n_local] holds the input.  Result in
+        Z_ext[:n_local].  Value-free Y-space iteration as on one GPU (epilogues PPNP_EPI_*)."""
+        from . import _lib
+        t = self.topo
+        on_gpu = self.comm_stream is not None
+        cur = torch.cuda.current_stream() if on_gpu else None
+        src = H_ext
+        for k in range(1, K + 1):
+            dst = Z_ext if (K - k) % 2 == 0 else S_ext
+            if K == 1:
+                epi, use_vals = _lib.EPI_PLAIN, True
+            elif k == 1:
+                epi, use_vals = _lib.EPI_Z2Y, True
+            elif k == K:
+                epi, use_vals = _lib.EPI_Y2Z, False
+            else:
+                epi, use_vals = _lib.EPI_Y, False
+            if self.overlap and on_gpu:
+                self.comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self.comm_stream):
+                    self.exchange.exchange(src)
+                if self.plans[0] is not None:
+                    self.plans[0].step(src, H_ext, dst, alpha, epi, use_vals)
+                cur.wait_stream(self.comm_stream)
+                if self.plans[1] is not None:
+                    self.plans[1].step(src, H_ext, dst, alpha, epi, use_vals)
+            elif self.overlap:
+                work = self.exchange.exchange(src, async_op=True)
+                if self.plans[0] is not None:
+                    self.plans[0].step(src, H_ext, dst, alpha, epi, use_vals)
+                if work is not None:
+                    work.wait()
+                if self.plans[1] is not None:
+                    self.plans[1].step(src, H_ext, dst, alpha, epi, use_vals)
+            else:
+                self.exchange.exchange(src)
+                self.plans[0].step(src, H_ext, dst, alpha, epi, use_vals)
+            src = dst
+        return Z_ext[: t.n_local]
+
+
+def build_stream_plan_subset(indptr, indices, vals, chunk_edges, order, n_rows_total):
+    """Edge stream over a subset of rows (``order``): the plan builder takes any row order; rows that
+    are left out simply never appear."""
+    from .plan import build_stream_plan
+    return build_stream_plan(indptr, indices, vals, chunk_edges, order, subset=True)
+
+
+class _SubGraph:
+    def __init__(self, plan, step_fn=None):
+        self.plan, self._step_fn = plan, step_fn
+        self._partial = {}
+
+    def step(self, Zin, T, Zout, alpha, epi, use_vals):
+        if self._step_fn is not None:
+            return self._step_fn(self.plan, Zin, T, Zout, alpha, epi, use_vals)
+        from . import _lib
+        lib = _lib.load()
+        F = Zin.shape[1]
+        partial = None
+        if self.plan.n_slots:
+            partial = self._partial.get(F)
+            if partial is None:
+                partial = torch.empty(self.plan.n_slots * F, dtype=torch.float32, device=Zin.device)
+                self._partial[F] = partial
+        rc = lib.ppnp_spmm_step(self.plan.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(Zout), _lib.ptr(partial),
+                                F, F, float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
+        _lib.check(rc, "ppnp_spmm_step")
+
+
+# ------------------------------------------------------------------------------ shard generation (bench)
+def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group=None):
+    """Rows of A + I of the R-MAT graph owned by ``rank`` (global column ids) and the partition.
+    Pass 1 estimates the per-row weight from the raw draws to place the boundaries by non-zeros;
+    pass 2 keeps the (de-duplicated) edges whose row falls inside this rank's block."""
+    from . import _lib
+    lib = _lib.load()
+
+    def keys_of(e0, e1):
+        k = torch.empty(2 * (e1 - e0), dtype=torch.int64, device=dev)
+        rc = lib.ppnp_rmat_keys(int(seed), int(scale), int(n), int(e0), int(e1), _lib.ptr(k), _lib.current_stream())
+        _lib.check(rc, "ppnp_rmat_keys")
+        return k[k >= 0]
+
+    # pass 1: this rank histograms its slice of the draws, all-reduce -> approximate degrees
+    w = torch.ones(n, dtype=torch.int32, device=dev)       # the self loop
+    per = (raw_draws + world - 1) // world
+    a, b = rank * per, min(raw_draws, (rank + 1) * per)
+    w_part = torch.zeros(n, dtype=torch.int32, device=dev)
+    for e0 in range(a, b, batch):
+        k = keys_of(e0, min(b, e0 + batch))
+        w_part += torch.bincount(k >> 32, minlength=n).to(torch.int32)
+        del k
+    if world > 1:
+        dist.all_reduce(w_part, group=group)
+    w += w_part
+    del w_part
+    bounds = balanced_row_blocks(w, world)
+    del w
+    lo, hi = bounds[rank], bounds[rank + 1]
+    # pass 2: all draws, keep my rows
+    kept = [(torch.arange(lo, hi, device=dev, dtype=torch.int64) << 32) | torch.arange(lo, hi, device=dev, dtype=torch.int64)]
+    pending = 0
+    for e0 in range(0, raw_draws, batch):
+        k = keys_of(e0, min(raw_draws, e0 + batch))
+        k = k[(k >= (lo << 32)) & (k < (hi << 32))]
+        kept.append(k)
+        pending += k.numel()
+        if pending > (1 << 28):                              # compact now and then to bound memory
+            kept = [torch.unique(torch.cat(kept))]
+            pending = 0
+    keys = torch.unique(torch.cat(kept), sorted=True)
+    del kept
+    rows = (keys >> 32) - lo
+    cols = (keys & 0xFFFFFFFF)
+    del keys
+    counts = torch.bincount(rows, minlength=hi - lo)
+    indptr = torch.zeros(hi - lo + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(counts, 0)
+    return indptr, cols, bounds
+
+
+def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
+    """D^-1/2 for ALL rows (fp32 [n]) from every rank's exact local degrees (all_gather)."""
+    n = bounds[-1]
+    deg_local = (indptr_local[1:] - indptr_local[:-1]).to(torch.float32)
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    if world == 1:
+        out.copy_(deg_local)
+    else:
+        # blocks have different lengths: gather padded to the longest block, then slice
+        width = max(bounds[r + 1] - bounds[r] for r in range(world))
+        mine = torch.ones(width, dtype=torch.float32, device=dev)
+        mine[: deg_local.numel()] = deg_local
+        allb = torch.empty(world * width, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(allb, mine, group=group)
+        for r in range(world):
+            out[bounds[r]: bounds[r + 1]] = allb[r * width: r * width + (bounds[r + 1] - bounds[r])]
+    return 1.0 / torch.sqrt(out)
+
+
+def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, overlap=True):
+    """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
+    row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
+    import time
+    t0 = time.perf_counter()
+    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world)
+    dinv = global_dinv(indptr, bounds, rank, world, dev)
+    topo = build_shard_topology(indptr, cols, bounds, rank)
+    del cols
+    prop = PartitionedPropagation(topo, dinv, overlap=overlap)
+    del dinv
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t0
+    n_ext = prop.n_ext()
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    H = torch.zeros(n_ext, F, device=dev)
+    G = torch.zeros(n_ext, F, device=dev)
+    H[: topo.n_local].normal_(generator=g)
+    G[: topo.n_local].normal_(generator=g)
+    Z, S = torch.empty_like(H), torch.empty_like(H)
+
+    def one_pass():
+        prop.propagate(H, Z, S, K, alpha)
+        prop.propagate(G, Z, S, K, alpha)
+
+    for _ in range(warmup):
+        one_pass()
+    torch.cuda.synchronize()
+    dist.barrier()
+    import bench as _bench
+    sampler = _bench.ClockSampler(dev.index)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.finish()
+    dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+
+    # e2e: host shards in, host results out
+    Hh = torch.empty((topo.n_local, F), dtype=torch.float32, pin_memory=True).copy_(H[: topo.n_local])
+    Zh = torch.empty((topo.n_local, F), dtype=torch.float32, pin_memory=True)
+
+    def one_pass_e2e():
+        for _ in range(2):
+            H[: topo.n_local].copy_(Hh, non_blocking=True)
+            prop.propagate(H, Z, S, K, alpha)
+            Zh.copy_(Z[: topo.n_local], non_blocking=True)
+
+    one_pass_e2e()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record()
+    for _ in range(2):
+        one_pass_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1) / 2], device=dev)
+    dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+
+    stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum()),
+                          sum(prop.exchange.send_counts)], dtype=torch.int64, device=dev)
+    allstats = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(allstats, stats)
+    nnz = int(sum(int(s[0]) for s in allstats))
+    launches = 0
+    for p in prop.plans:
+        if p is not None:
+            launches += 2 if p.plan.n_fix > 0 else 1
+    work = 2 * K * nnz * F
+    return {
+        "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,
+        "partition": {"rule": "contiguous row blocks cut at the non-zero prefix sum", "overlap": bool(overlap),
+                      "rows": [int(s[2]) for s in allstats], "nnz": [int(s[0]) for s in allstats],
+                      "halo_rows": [int(s[1]) for s in allstats], "interior_rows": [int(s[3]) for s in allstats],
+                      "sent_rows_per_step": [int(s[4]) for s in allstats]},
+        "e2e": {"value": work / (float(ms_e2e) * 1e-3), "unit": "edge*feature/s", "ms_per_step": float(ms_e2e),
+                "h2d_bytes_per_step": 2 * n * F * 4, "d2h_bytes_per_step": 2 * n * F * 4},
+        "gpu_launches": launches * 2 * K * steps, "graph_build_s": round(t_build, 1),
+        "halo_bytes_per_step_rank0": prop.exchange.bytes_per_step(F),
+    }

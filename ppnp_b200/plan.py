@@ -80,11 +80,13 @@ class StreamPlan:
                           mv(self.fix_deg), self.n_slots, mv(self.order), self.n_segs_real)
 
 
-def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None):
+def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None, subset=False):
     """Cut the CSR (indptr[n+1], indices[nnz], optional vals[nnz]) into the edge stream.
 
-    ``order`` (int64 [n], a permutation) is the processing order of the rows; column ids are
-    never relabelled, so inputs and outputs of the propagation keep the caller's row order.
+    ``order`` (int64, a permutation of the rows) is the processing order; column ids are never
+    relabelled, so inputs and outputs of the propagation keep the caller's row order.  With
+    ``subset=True`` ``order`` may list only some rows: the stream then produces exactly those rows
+    (used to split a shard into interior and boundary rows, ppnp_b200/dist.py).
     """
     if chunk_edges % 128 != 0 or chunk_edges <= 0:
         raise ValueError("chunk_edges must be a positive multiple of 128")
@@ -99,6 +101,7 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None):
     if bool((deg <= 0).any()):
         raise ValueError("every row of A_hat needs at least its self loop")
 
+    n_rows_total = n
     if order is None:
         L = deg
         a = ip[:-1]
@@ -107,8 +110,12 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None):
         stream_vals = vals
     else:
         order = order.to(device=dev, dtype=torch.int64)
+        if not subset and order.numel() != n:
+            raise ValueError("order must list every row once (pass subset=True for a partial stream)")
         L = deg[order]
         a = torch.cumsum(L, 0) - L
+        nnz = int(L.sum().item())
+        n = int(order.numel())
         # source position of every stream edge
         src = torch.repeat_interleave(ip[:-1][order] - a, L) + torch.arange(nnz, device=dev, dtype=torch.int64)
         stream_cols = indices[src].to(torch.int32)
@@ -165,7 +172,7 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None):
     if fix_rows_pos.numel():
         fp[1:] = torch.cumsum(pieces[fix_rows_pos], 0)
     fix_deg = L[fix_rows_pos].to(torch.float32)
-    return StreamPlan(n=n, nnz=nnz, chunk_edges=W, n_chunks=n_chunks, cols=cols, vals=svals, seg_row=seg_row,
+    return StreamPlan(n=n_rows_total, nnz=nnz, chunk_edges=W, n_chunks=n_chunks, cols=cols, vals=svals, seg_row=seg_row,
                       chunk_seg=chunk_seg, fix_ptr=fp.to(torch.int32), fix_row=fix_row, fix_deg=fix_deg,
                       n_slots=n_slots, order=order, n_segs_real=n_real_segs)
 

@@ -1,0 +1,103 @@
+"""Host-side logic of the row-partitioned multi-GPU propagation (ppnp_b200/dist.py) on CPU with the
+gloo backend, world sizes 2 and 3: partition by non-zero prefix, column remap, halo lists, the
+all-to-all exchange and the step orchestration (interior/boundary split, Y-space epilogues).  The
+local arithmetic is the numpy walker of the edge stream (tests/util.py); the CUDA kernel itself is
+covered by the -m gpu tests."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from util import ROOT, oracle, relerr, epi_coef
+
+
+def walker_step(plan, Zin, T, Zout, alpha, epi, use_vals):
+    """numpy stand-in for ppnp_spmm_step over a (subset) plan: writes only the rows the plan produces."""
+    cols = plan.cols.numpy(); vals = plan.vals.numpy() if plan.vals is not None else None
+    seg_row = plan.seg_row.numpy(); chunk_seg = plan.chunk_seg.numpy(); W = plan.chunk_edges
+    Zi = Zin.numpy().astype(np.float64); Tn = T.numpy().astype(np.float64)
+    F = Zi.shape[1]
+    partial = np.zeros((max(plan.n_slots, 1), F))
+    for c in range(plan.n_chunks):
+        s = int(chunk_seg[c]); acc = np.zeros(F); cnt = 0
+        for e in range(c * W, (c + 1) * W):
+            raw = int(cols[e]); col = raw & 0x7FFFFFFF
+            acc += (vals[e] if use_vals else 1.0) * Zi[col]; cnt += 1
+            if raw < 0:
+                sv = int(seg_row[s]); s += 1
+                if sv < 0:
+                    partial[sv & 0x7FFFFFFF] = acc
+                else:
+                    a, b = epi_coef(epi, alpha, cnt)
+                    Zout[sv] = torch.from_numpy((a * acc + b * Tn[sv]).astype(np.float32))
+                acc = np.zeros(F); cnt = 0
+    fp, fr, fd = plan.fix_ptr.numpy(), plan.fix_row.numpy(), plan.fix_deg.numpy()
+    for q in range(plan.n_fix):
+        a, b = epi_coef(epi, alpha, float(fd[q]))
+        Zout[fr[q]] = torch.from_numpy((a * partial[fp[q]:fp[q + 1]].sum(0) + b * Tn[fr[q]]).astype(np.float32))
+
+
+def worker(rank, world, port, overlap, outdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ppnp_b200 import dist as pd
+        n, F, K, alpha = 1500, 5, 4, 0.1
+        ip, idx = oracle.rmat_graph(n, 20000, 11, seed=5)
+        oip, oidx, oval, odeg = oracle.c_a_hat(ip, idx, None, "sym")          # A + I structure, global columns
+        deg = torch.from_numpy(np.diff(oip))
+        bounds = pd.balanced_row_blocks(deg, world)
+        assert bounds[0] == 0 and bounds[-1] == n and all(b1 >= b0 for b0, b1 in zip(bounds, bounds[1:]))
+        nnz_blocks = [int(oip[bounds[r + 1]] - oip[bounds[r]]) for r in range(world)]
+        assert max(nnz_blocks) < 1.5 * (oip[-1] / world) + deg.max().item()   # balanced by non-zeros
+        lo, hi = bounds[rank], bounds[rank + 1]
+        ipl = torch.from_numpy(oip[lo:hi + 1] - oip[lo])
+        colsg = torch.from_numpy(oidx[oip[lo]:oip[hi]].astype(np.int64))
+        topo = pd.build_shard_topology(ipl, colsg, bounds, rank)
+        # remap is invertible and the halo is exactly the set of remote columns
+        ext_ids = torch.cat([torch.arange(lo, hi), topo.halo_cols])
+        assert torch.equal(ext_ids[topo.indices.long()], colsg)
+        assert sum(topo.recv_counts) == topo.n_halo
+        dinv = pd.global_dinv(ipl, bounds, rank, world, torch.device("cpu"))
+        assert np.allclose(dinv.numpy(), 1 / np.sqrt(odeg))
+        prop = pd.PartitionedPropagation(topo, dinv, chunk_edges=128, overlap=overlap, step_fn=walker_step)
+        rng = np.random.RandomState(0)
+        Hg = rng.randn(n, F).astype(np.float32)                                # the same global H on every rank
+        n_ext = prop.n_ext()
+        H = torch.zeros(n_ext, F); H[: topo.n_local] = torch.from_numpy(Hg[lo:hi])
+        Z, S = torch.zeros_like(H), torch.zeros_like(H)
+        out = prop.propagate(H, Z, S, K, alpha)
+        import scipy.sparse as sp
+        A = sp.csr_matrix((oval, oidx, oip), shape=(n, n))
+        ref = oracle.appnp(A, Hg.astype(np.float64), alpha, K)[lo:hi]
+        err = relerr(out.numpy(), ref)
+        assert err < 1e-5, err
+        # K = 1 path (plain epilogue)
+        out1 = prop.propagate(H, Z, S, 1, alpha)
+        assert relerr(out1.numpy(), oracle.appnp(A, Hg.astype(np.float64), alpha, 1)[lo:hi]) < 1e-5
+        with open(os.path.join(outdir, f"ok_{rank}"), "w") as f:
+            f.write(f"{err}\n")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,overlap", [(2, True), (2, False), (3, True)])
+def test_partitioned_propagation_gloo(tmp_path, world, overlap):
+    port = 29600 + world * 10 + int(overlap) + (os.getpid() % 50)
+    mp.spawn(worker, args=(world, port, overlap, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok_{r}") for r in range(world))
+
+
+def test_balanced_row_blocks_handles_skew():
+    from ppnp_b200.dist import balanced_row_blocks
+    w = torch.ones(1000, dtype=torch.int64)
+    w[:10] = 1000
+    b = balanced_row_blocks(w, 4)
+    sums = [int(w[b[i]:b[i + 1]].sum()) for i in range(4)]
+    assert b[0] == 0 and b[-1] == 1000 and max(sums) <= 2 * (int(w.sum()) // 4)
+    assert balanced_row_blocks(torch.ones(5), 8)[-1] == 5      # more ranks than rows: empty blocks allowed
