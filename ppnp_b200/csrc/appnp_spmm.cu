@@ -25,6 +25,12 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef PPNP_SPMM_MINBLOCKS
 #define PPNP_SPMM_MINBLOCKS 4   // resident 256-thread CTAs per SM the register budget is capped for
 #endif
+#ifndef PPNP_SPMM_MINBLOCKS_WIDE
+#define PPNP_SPMM_MINBLOCKS_WIDE 3   // same, for the variants that carry several index registers or values
+#endif
+#ifndef PPNP_SPMM_RING
+#define PPNP_SPMM_RING 8        // gathers kept in flight per lane on the rolling path
+#endif
 #ifndef PPNP_SPMM_U4
 #define PPNP_SPMM_U4 4          // float4 gathers issued back to back per group (VEC == 4)
 #endif
@@ -45,11 +51,13 @@ __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t
     }
 }
 
-// A slab is G consecutive edges of the chunk, one column index per lane of the group.  Slabs are
-// software-pipelined three deep: indices of slab j+2 in flight, segment rows of slab j+1 in
-// flight, gathers of slab j being issued.
+// A slab is SE = SR * G consecutive edges of the chunk (16 edges, 32 for G = 32): SR index
+// registers per lane, register r of lane l holding edge r * G + l.  Slabs are software-pipelined
+// three deep: indices of slab j+2 in flight, segment rows of slab j+1 in flight, gathers of slab j
+// being issued.  A slab without any segment end (warp-wide) takes the rolling path: RING gathers
+// stay in flight per lane, each accumulate immediately re-arms its register with the next gather.
 template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE>
-__global__ void __launch_bounds__(256, PPNP_SPMM_MINBLOCKS)
+__global__ void __launch_bounds__(256, (G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOCKS : PPNP_SPMM_MINBLOCKS_WIDE)
 spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
                    const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
                    int64_t n_chunks, int chunk_edges,
@@ -57,8 +65,12 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
                    float* __restrict__ Zout, float* __restrict__ partial,
                    int ld, int F, float alpha, int epi) {
     using V = Vec<VEC>;
-    constexpr int GPW = 32 / G;      // groups per warp
-    static_assert(G % U == 0, "sub-batch must divide the slab");
+    constexpr int GPW = 32 / G;                     // groups per warp
+    constexpr int SR = (G >= 16) ? 1 : 16 / G;      // index registers per lane and slab
+    constexpr int SE = SR * G;                      // edges per slab
+    constexpr int RING = (SE >= PPNP_SPMM_RING) ? PPNP_SPMM_RING : SE;
+    static_assert(G % U == 0, "sub-batch must divide the register slab");
+    static_assert(SE % RING == 0, "ring must divide the slab");
 
     const int lane = threadIdx.x & 31;
     const int g = lane / G;
@@ -78,7 +90,7 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
     const char* zbase = reinterpret_cast<const char*>(Zin + f);
     const char* tbase = reinterpret_cast<const char*>(T + f);
     const unsigned row_bytes = (unsigned)ld * 4u;
-    const int n_slabs = chunk_edges / G;
+    const int n_slabs = chunk_edges / SE;
 
     for (int64_t c = warp_global * GPW + g; c < n_chunks; c += total_groups) {
         int s = __ldg(chunk_seg + c);
@@ -88,79 +100,125 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
         int seg_begin = 0;  // chunk-local position where the running segment started
 
         // pipeline prologue: slab 0 -> stage 1 (indices known, segment rows requested), slab 1 -> stage 2
-        int raw1 = __ldcs(cp);
-        float w1 = HAS_VAL ? __ldcs(vp) : 0.f;
-        int raw2 = __ldcs(cp + G);
-        float w2 = HAS_VAL ? __ldcs(vp + G) : 0.f;
-        unsigned ends1 = (__ballot_sync(FULL, raw1 < 0) >> gshift) & gbits;
-        // unconditional (seg_row is padded): no predicated merge, so nothing waits on this load
-        // until the slab that needs it is processed
-        int segv1 = __ldcs(seg_row + s + __popc(ends1 & lt));
-        s += __popc(ends1);
+        int raw1[SR], raw2[SR], segv1[SR];
+        float w1[SR], w2[SR];
+        unsigned ends1[SR];
+#pragma unroll
+        for (int r = 0; r < SR; ++r) {
+            raw1[r] = __ldcs(cp + r * G);
+            raw2[r] = __ldcs(cp + SE + r * G);
+            if (HAS_VAL) { w1[r] = __ldcs(vp + r * G); w2[r] = __ldcs(vp + SE + r * G); }
+        }
+#pragma unroll
+        for (int r = 0; r < SR; ++r) {
+            ends1[r] = (__ballot_sync(FULL, raw1[r] < 0) >> gshift) & gbits;
+            // unconditional (seg_row is padded): no predicated merge, nothing waits on this load
+            // until the slab that needs it is processed
+            segv1[r] = __ldcs(seg_row + s + __popc(ends1[r] & lt));
+            s += __popc(ends1[r]);
+        }
 
 #pragma unroll 1
         for (int j = 0; j < n_slabs; ++j) {
-            const int raw0 = raw1;
-            const float w0 = w1;
-            const unsigned ends0 = ends1;
-            const int segv0 = segv1;
+            int raw0[SR], segv0[SR];
+            float w0[SR];
+            unsigned ends0[SR];
+            unsigned any_end = 0;
+#pragma unroll
+            for (int r = 0; r < SR; ++r) {
+                raw0[r] = raw1[r]; segv0[r] = segv1[r]; ends0[r] = ends1[r];
+                if (HAS_VAL) w0[r] = w1[r];
+                any_end |= ends0[r];
+            }
             // stage 1 <- stage 2
-            raw1 = raw2;
-            w1 = w2;
-            ends1 = (__ballot_sync(FULL, raw1 < 0) >> gshift) & gbits;
-            if (j + 1 >= n_slabs) ends1 = 0;   // past the chunk: the replayed slab is never processed
-            segv1 = __ldcs(seg_row + s + __popc(ends1 & lt));
-            s += __popc(ends1);
+#pragma unroll
+            for (int r = 0; r < SR; ++r) {
+                raw1[r] = raw2[r];
+                if (HAS_VAL) w1[r] = w2[r];
+                ends1[r] = (__ballot_sync(FULL, raw1[r] < 0) >> gshift) & gbits;
+                if (j + 1 >= n_slabs) ends1[r] = 0;   // past the chunk: the replayed slab is never processed
+                segv1[r] = __ldcs(seg_row + s + __popc(ends1[r] & lt));
+                s += __popc(ends1[r]);
+            }
             // stage 2 <- memory (clamped to the last slab of the chunk: always a valid address)
             {
                 const int jn = (j + 2 < n_slabs) ? j + 2 : n_slabs - 1;
-                raw2 = __ldcs(cp + jn * G);
-                if (HAS_VAL) w2 = __ldcs(vp + jn * G);
+#pragma unroll
+                for (int r = 0; r < SR; ++r) {
+                    raw2[r] = __ldcs(cp + jn * SE + r * G);
+                    if (HAS_VAL) w2[r] = __ldcs(vp + jn * SE + r * G);
+                }
             }
 
+            if (!__any_sync(FULL, any_end != 0)) {
+                // ---- rolling path: no segment end in this slab for any group of the warp
+                V v[RING];
+                float wv[RING];
 #pragma unroll
-            for (int u0 = 0; u0 < G; u0 += U) {
-                const unsigned sub = (ends0 >> u0) & ((1u << U) - 1u);
-                if (!__any_sync(FULL, sub != 0)) {   // warp-uniform: no group of this warp ends a segment here
-                    // ---- fast path: no segment ends among these U edges
-                    V v[U];
+                for (int e = 0; e < RING; ++e) {
+                    const int col = __shfl_sync(FULL, raw0[e / G], e % G, G);
+                    if (HAS_VAL) wv[e] = __shfl_sync(FULL, w0[e / G], e % G, G);
+                    v[e].zero();
+                    if (active) v[e] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int col = __shfl_sync(FULL, raw0, u0 + u, G);
-                        v[u].zero();
-                        if (active) v[u] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
-                    }
+                for (int e = RING; e < SE; ++e) {
+                    if (HAS_VAL) acc.fma(wv[e % RING], v[e % RING]); else acc.add(v[e % RING]);
+                    const int col = __shfl_sync(FULL, raw0[e / G], e % G, G);
+                    if (HAS_VAL) wv[e % RING] = __shfl_sync(FULL, w0[e / G], e % G, G);
+                    if (active) v[e % RING] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (HAS_VAL) acc.fma(__shfl_sync(FULL, w0, u0 + u, G), v[u]); else acc.add(v[u]);
-                    }
-                } else {
-                    // ---- general path: some of these edges finish a segment
-                    V v[U], t[U];
-                    int ru[U], sv[U];
+                for (int e = 0; e < RING; ++e) {
+                    if (HAS_VAL) acc.fma(wv[e], v[e]); else acc.add(v[e]);
+                }
+            } else {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        ru[u] = __shfl_sync(FULL, raw0, u0 + u, G);
-                        sv[u] = __shfl_sync(FULL, segv0, u0 + u, G);
-                        v[u].zero();
-                        t[u].zero();
-                        if (active) v[u] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)(ru[u] & 0x7fffffff) * row_bytes));
-                        if (active && ru[u] < 0 && sv[u] >= 0) t[u] = V::load_stream(reinterpret_cast<const float*>(tbase + (uint64_t)(unsigned)sv[u] * row_bytes));
-                    }
+              for (int r = 0; r < SR; ++r) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (HAS_VAL) acc.fma(__shfl_sync(FULL, w0, u0 + u, G), v[u]); else acc.add(v[u]);
-                        if (ru[u] < 0) {
-                            const int pos = j * G + u0 + u;
-                            {   // copies: the out-of-line call takes references, acc itself must stay in registers
-                                const V a2 = acc, t2 = t[u];
-                                emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi);
+                for (int u0 = 0; u0 < G; u0 += U) {
+                    const unsigned sub = (ends0[r] >> u0) & ((1u << U) - 1u);
+                    if (!__any_sync(FULL, sub != 0)) {   // warp-uniform: no group of this warp ends a segment here
+                        V v[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int col = __shfl_sync(FULL, raw0[r], u0 + u, G);
+                            v[u].zero();
+                            if (active) v[u] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (HAS_VAL) acc.fma(__shfl_sync(FULL, w0[r], u0 + u, G), v[u]); else acc.add(v[u]);
+                        }
+                    } else {
+                        // ---- general path: some of these edges finish a segment
+                        V v[U], t[U];
+                        int ru[U], sv[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            ru[u] = __shfl_sync(FULL, raw0[r], u0 + u, G);
+                            sv[u] = __shfl_sync(FULL, segv0[r], u0 + u, G);
+                            v[u].zero();
+                            t[u].zero();
+                            if (active) v[u] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)(ru[u] & 0x7fffffff) * row_bytes));
+                            if (active && ru[u] < 0 && sv[u] >= 0) t[u] = V::load_stream(reinterpret_cast<const float*>(tbase + (uint64_t)(unsigned)sv[u] * row_bytes));
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            if (HAS_VAL) acc.fma(__shfl_sync(FULL, w0[r], u0 + u, G), v[u]); else acc.add(v[u]);
+                            if (ru[u] < 0) {
+                                const int pos = j * SE + r * G + u0 + u;
+                                {   // copies: the out-of-line call takes references, acc itself must stay in registers
+                                    const V a2 = acc, t2 = t[u];
+                                    emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi);
+                                }
+                                acc.zero();
+                                seg_begin = pos + 1;
                             }
-                            acc.zero();
-                            seg_begin = pos + 1;
                         }
                     }
                 }
+              }
             }
         }
     }

@@ -89,10 +89,11 @@ __device__ __forceinline__ void epi_coef(int epi, float alpha, float deg, float&
     switch (epi) {
         default:
         case PPNP_EPI_PLAIN: a = oma; b = alpha; break;
-        case PPNP_EPI_Z2Y: { const float d = 1.0f / sqrtf(deg); a = oma * d; b = alpha * d; } break;
-        case PPNP_EPI_Y: a = oma / deg; b = alpha / sqrtf(deg); break;
-        case PPNP_EPI_Y2Z: a = oma / sqrtf(deg); b = alpha; break;
-        case PPNP_EPI_RW: a = oma / deg; b = alpha; break;
+        // rsqrtf / __frcp_rn: one MUFU each (<= 2 ulp / correctly rounded); deg is a small integer
+        case PPNP_EPI_Z2Y: { const float d = rsqrtf(deg); a = oma * d; b = alpha * d; } break;
+        case PPNP_EPI_Y: a = oma * __frcp_rn(deg); b = alpha * rsqrtf(deg); break;
+        case PPNP_EPI_Y2Z: a = oma * rsqrtf(deg); b = alpha; break;
+        case PPNP_EPI_RW: a = oma * __frcp_rn(deg); b = alpha; break;
     }
 }
 

@@ -375,6 +375,27 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     ms_e2e = torch.tensor([e0.elapsed_time(e1) / 2], device=dev)
     dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
 
+    # diagnostics: the exchange alone and the compute alone (not part of the headline number)
+    def timed(fn, reps=5):
+        torch.cuda.synchronize(); dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    from . import _lib as _l
+    ms_exchange = timed(lambda: prop.exchange.exchange(Z))
+
+    def compute_only():
+        for p in prop.plans:
+            if p is not None:
+                p.step(Z, H, S, alpha, _l.EPI_Y, False)
+    ms_compute = timed(compute_only)
+
     stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum()),
                           sum(prop.exchange.send_counts)], dtype=torch.int64, device=dev)
     allstats = [torch.empty_like(stats) for _ in range(world)]
@@ -395,4 +416,5 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
                 "h2d_bytes_per_step": 2 * n * F * 4, "d2h_bytes_per_step": 2 * n * F * 4},
         "gpu_launches": launches * 2 * K * steps, "graph_build_s": round(t_build, 1),
         "halo_bytes_per_step_rank0": prop.exchange.bytes_per_step(F),
+        "exchange_ms_alone": ms_exchange, "spmm_step_ms_alone": ms_compute,
     }
