@@ -51,11 +51,33 @@ __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t
     }
 }
 
-// A slab is SE = SR * G consecutive edges of the chunk (16 edges, 32 for G = 32): SR index
-// registers per lane, register r of lane l holding edge r * G + l.  Slabs are software-pipelined
-// three deep: indices of slab j+2 in flight, segment rows of slab j+1 in flight, gathers of slab j
-// being issued.  A slab without any segment end (warp-wide) takes the rolling path: RING gathers
-// stay in flight per lane, each accumulate immediately re-arms its register with the next gather.
+// A slab is SE = SR * G consecutive edges of the chunk (16 edges, 32 for G = 32): SR index words per
+// lane, word r of lane l being edge r * G + l.
+//
+// Index traffic never touches registers before it is needed: every lane cp.async's its own index
+// words (and values) of slab j + 2*PD and its segment-row words of slab j + PD into private
+// shared-memory slots and reads them back with LDS once `cp.async.wait_group` says they have
+// landed -- a prefetch distance of PD slabs for both streams with no in-flight register to move or
+// spill (a register-based pipeline stalls on exactly those moves, profiles/r01_prof_spmm4).
+// A slab without any segment end (warp-wide) takes the rolling path: RING gathers stay in flight per
+// lane, each accumulate immediately re-arms its register with the next gather.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int G>
+struct StageCfg {
+    static constexpr int SR = (G >= 16) ? 1 : 16 / G;   // index words per lane and slab
+    static constexpr int PD = (SR == 1) ? 2 : 1;        // prefetch distance in slabs
+    static constexpr int ISLOTS = (PD == 2) ? 8 : 4;    // >= 2*PD + 1, power of two
+    static constexpr int SSLOTS = (PD == 2) ? 4 : 2;    // >= PD + 1, power of two
+    static constexpr int words_per_thread(bool has_val) { return SR * (ISLOTS * (has_val ? 2 : 1) + SSLOTS); }
+};
+
 template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE>
 __global__ void __launch_bounds__(256, (G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOCKS : PPNP_SPMM_MINBLOCKS_WIDE)
 spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
@@ -65,14 +87,23 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
                    float* __restrict__ Zout, float* __restrict__ partial,
                    int ld, int F, float alpha, int epi) {
     using V = Vec<VEC>;
+    using SC = StageCfg<G>;
     constexpr int GPW = 32 / G;                     // groups per warp
-    constexpr int SR = (G >= 16) ? 1 : 16 / G;      // index registers per lane and slab
+    constexpr int SR = SC::SR;
     constexpr int SE = SR * G;                      // edges per slab
+    constexpr int PD = SC::PD, ISLOTS = SC::ISLOTS, SSLOTS = SC::SSLOTS;
     constexpr int RING = (SE >= PPNP_SPMM_RING) ? PPNP_SPMM_RING : SE;
     static_assert(G % U == 0, "sub-batch must divide the register slab");
     static_assert(SE % RING == 0, "ring must divide the slab");
 
-    const int lane = threadIdx.x & 31;
+    // private staging slots, [slot][word r][thread]: conflict-free, no cross-thread visibility needed
+    extern __shared__ int32_t stage[];
+    const int tid = threadIdx.x;
+    int32_t* s_idx = stage + tid;                                   // + (slot * SR + r) * 256
+    int32_t* s_seg = stage + ISLOTS * SR * 256 + tid;               // + (slot * SR + r) * 256
+    float* s_val = reinterpret_cast<float*>(stage + (ISLOTS + SSLOTS) * SR * 256) + tid;
+
+    const int lane = tid & 31;
     const int g = lane / G;
     const int lg = lane % G;
     // The groups of a warp run in lock step (same trip counts everywhere), so shuffles and ballots
@@ -81,7 +112,7 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
     const unsigned gbits = (G == 32) ? FULL : ((1u << G) - 1u);
     const unsigned lt = (1u << lg) - 1u;  // lower lanes of my group (after shifting the ballot down)
 
-    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + tid) >> 5;
     const int64_t total_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * GPW;
 
     const int f = ((int)blockIdx.y * G + lg) * VEC;
@@ -93,60 +124,73 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
     const int n_slabs = chunk_edges / SE;
 
     for (int64_t c = warp_global * GPW + g; c < n_chunks; c += total_groups) {
-        int s = __ldg(chunk_seg + c);
+        int s = __ldg(chunk_seg + c);       // next segment whose row has not been requested yet
         const int32_t* cp = cols + c * (int64_t)chunk_edges + lg;
         const float* vp = HAS_VAL ? vals + c * (int64_t)chunk_edges + lg : nullptr;
         V acc; acc.zero();
         int seg_begin = 0;  // chunk-local position where the running segment started
 
-        // pipeline prologue: slab 0 -> stage 1 (indices known, segment rows requested), slab 1 -> stage 2
-        int raw1[SR], raw2[SR], segv1[SR];
-        float w1[SR], w2[SR];
-        unsigned ends1[SR];
+        // ---- prologue: indices of slabs 0 .. 2*PD-1, then segment rows of slabs 0 .. PD-1
 #pragma unroll
-        for (int r = 0; r < SR; ++r) {
-            raw1[r] = __ldcs(cp + r * G);
-            raw2[r] = __ldcs(cp + SE + r * G);
-            if (HAS_VAL) { w1[r] = __ldcs(vp + r * G); w2[r] = __ldcs(vp + SE + r * G); }
-        }
+        for (int t = 0; t < 2 * PD; ++t) {
+            const int jt = (t < n_slabs) ? t : n_slabs - 1;
 #pragma unroll
-        for (int r = 0; r < SR; ++r) {
-            ends1[r] = (__ballot_sync(FULL, raw1[r] < 0) >> gshift) & gbits;
-            // unconditional (seg_row is padded): no predicated merge, nothing waits on this load
-            // until the slab that needs it is processed
-            segv1[r] = __ldcs(seg_row + s + __popc(ends1[r] & lt));
-            s += __popc(ends1[r]);
+            for (int r = 0; r < SR; ++r) {
+                cp_async4(s_idx + ((t % ISLOTS) * SR + r) * 256, cp + jt * SE + r * G);
+                if (HAS_VAL) cp_async4(s_val + ((t % ISLOTS) * SR + r) * 256, vp + jt * SE + r * G);
+            }
         }
+        cp_async_commit();
+        cp_async_wait<0>();
+#pragma unroll
+        for (int t = 0; t < PD; ++t) {
+#pragma unroll
+            for (int r = 0; r < SR; ++r) {
+                const int raw = s_idx[((t % ISLOTS) * SR + r) * 256];
+                unsigned e = (__ballot_sync(FULL, raw < 0) >> gshift) & gbits;
+                if (t >= n_slabs) e = 0;
+                cp_async4(s_seg + ((t % SSLOTS) * SR + r) * 256, seg_row + s + __popc(e & lt));
+                s += __popc(e);
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();   // slab 0's segment rows are read in the first iteration
 
 #pragma unroll 1
         for (int j = 0; j < n_slabs; ++j) {
+            // everything but the PD-1 newest groups has landed: indices up to slab j+PD, segment rows up to slab j
+            cp_async_wait<PD - 1>();
+            // request: indices of slab j+2PD, segment rows of slab j+PD
+            {
+                const int ji = (j + 2 * PD < n_slabs) ? j + 2 * PD : n_slabs - 1;
+                const int si = (j + 2 * PD) & (ISLOTS - 1);
+                const int sn = (j + PD) & (ISLOTS - 1), ss = (j + PD) & (SSLOTS - 1);
+#pragma unroll
+                for (int r = 0; r < SR; ++r) {
+                    cp_async4(s_idx + (si * SR + r) * 256, cp + ji * SE + r * G);
+                    if (HAS_VAL) cp_async4(s_val + (si * SR + r) * 256, vp + ji * SE + r * G);
+                    const int rawn = s_idx[(sn * SR + r) * 256];
+                    unsigned e = (__ballot_sync(FULL, rawn < 0) >> gshift) & gbits;
+                    if (j + PD >= n_slabs) e = 0;      // past the chunk: the replayed slab is never processed
+                    cp_async4(s_seg + (ss * SR + r) * 256, seg_row + s + __popc(e & lt));
+                    s += __popc(e);
+                }
+                cp_async_commit();
+            }
+            // the slab to process
             int raw0[SR], segv0[SR];
             float w0[SR];
             unsigned ends0[SR];
             unsigned any_end = 0;
-#pragma unroll
-            for (int r = 0; r < SR; ++r) {
-                raw0[r] = raw1[r]; segv0[r] = segv1[r]; ends0[r] = ends1[r];
-                if (HAS_VAL) w0[r] = w1[r];
-                any_end |= ends0[r];
-            }
-            // stage 1 <- stage 2
-#pragma unroll
-            for (int r = 0; r < SR; ++r) {
-                raw1[r] = raw2[r];
-                if (HAS_VAL) w1[r] = w2[r];
-                ends1[r] = (__ballot_sync(FULL, raw1[r] < 0) >> gshift) & gbits;
-                if (j + 1 >= n_slabs) ends1[r] = 0;   // past the chunk: the replayed slab is never processed
-                segv1[r] = __ldcs(seg_row + s + __popc(ends1[r] & lt));
-                s += __popc(ends1[r]);
-            }
-            // stage 2 <- memory (clamped to the last slab of the chunk: always a valid address)
             {
-                const int jn = (j + 2 < n_slabs) ? j + 2 : n_slabs - 1;
+                const int s0 = j & (ISLOTS - 1), q0 = j & (SSLOTS - 1);
 #pragma unroll
                 for (int r = 0; r < SR; ++r) {
-                    raw2[r] = __ldcs(cp + jn * SE + r * G);
-                    if (HAS_VAL) w2[r] = __ldcs(vp + jn * SE + r * G);
+                    raw0[r] = s_idx[(s0 * SR + r) * 256];
+                    segv0[r] = s_seg[(q0 * SR + r) * 256];
+                    if (HAS_VAL) w0[r] = s_val[(s0 * SR + r) * 256];
+                    ends0[r] = (__ballot_sync(FULL, raw0[r] < 0) >> gshift) & gbits;
+                    any_end |= ends0[r];
                 }
             }
 
@@ -221,6 +265,7 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
               }
             }
         }
+        cp_async_wait<0>();   // nothing of this chunk may land after its slots are reused
     }
 }
 
@@ -265,9 +310,10 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 template <typename K>
-int blocks_per_sm(K kernel, int threads) {
+int blocks_per_sm(K kernel, int threads, int smem_bytes) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess || nb < 1) nb = 1;
+    if (smem_bytes > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem_bytes) != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
 
@@ -285,10 +331,11 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
     do {                                                                                                           \
         auto k = spmm_stream_kernel<VEC, G, HV_, U, FT_>;                                                          \
         static thread_local int occ = 0;                                                                           \
-        if (!occ) occ = blocks_per_sm(k, THREADS);                                                                 \
+        const int smem_bytes = StageCfg<G>::words_per_thread(HV_) * THREADS * 4;                                   \
+        if (!occ) occ = blocks_per_sm(k, THREADS, smem_bytes);                                                     \
         const int64_t cap = (int64_t)sm_count() * occ;                                                             \
         dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)tiles);                                           \
-        k<<<grid, THREADS, 0, stream>>>(p->cols, HV_ ? p->vals : nullptr, p->seg_row, p->chunk_seg, p->n_chunks,   \
+        k<<<grid, THREADS, smem_bytes, stream>>>(p->cols, HV_ ? p->vals : nullptr, p->seg_row, p->chunk_seg, p->n_chunks, \
                                         p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi);            \
     } while (0)
     if (use_vals) { if (full_tile) PPNP_LAUNCH(true, true); else PPNP_LAUNCH(true, false); }
