@@ -38,6 +38,10 @@ extern "C" {
 #define PPNP_EPI_Y 2       /* a = (1-alpha)/d,        b = alpha/sqrt(d)    value-free, Y = D^-1/2 Z space  */
 #define PPNP_EPI_Y2Z 3     /* a = (1-alpha)/sqrt(d),  b = alpha            value-free, last step Y->Z      */
 #define PPNP_EPI_RW 4      /* a = (1-alpha)/d,        b = alpha            value-free 'rw' mode            */
+/* OR-ed onto one of the above: out[r] = a * acc_r + 1 * T[r] with T == Zout, i.e. the step ADDS its
+ * contribution to rows an earlier pass already wrote (multi-pass steps of the partitioned form,
+ * ppnp_b200/dist.py: local columns first, halo columns once they have arrived). */
+#define PPNP_EPI_ACC 16
 
 /* bit 31 of a stream column: last edge of its segment; of a seg_row entry: partial segment */
 #define PPNP_FLAG 0x80000000u
@@ -98,6 +102,8 @@ typedef struct ppnp_plan {
     const int32_t* fix_ptr;   /* [n_fix + 1] slot ranges                                */
     const int32_t* fix_row;   /* [n_fix]                                                */
     const float* fix_deg;     /* [n_fix] row degree (edge count incl. self loop)        */
+    const float* row_deg;     /* [n] or NULL: degree of every row, for streams that hold only
+                                 part of a row's edges (NULL: degree = edges of the segment) */
 } ppnp_plan_t;
 
 /* One step: out = a * (A_hat-or-(A+I)) Zin + b * T with the epilogue `epi`.
@@ -174,6 +180,14 @@ int ppnp_batch_propagate(const int64_t* indptr, const int32_t* indices, const fl
                          const int64_t* idx_batch, int64_t B, const int32_t* colmap,
                          const float* Hsub, int64_t ld_h, int32_t C, float* out, int64_t ld_out,
                          int32_t transpose, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) Partitioned propagation helper (BASELINE config 5; no counterpart in the single-process
+ *     reference): dst[i, :] = src[idx[i], :] for i < n_rows.  src may be a peer GPU's buffer mapped
+ *     over NVLink (halo pull) or the local Z (pack in front of an NCCL send).
+ * ---------------------------------------------------------------------------------------- */
+int ppnp_gather_rows(const float* src, int64_t ld_src, const int64_t* idx, int64_t n_rows, int32_t F,
+                     float* dst, int64_t ld_dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Synthetic-workload plumbing (BASELINE.json configs 4/5): R-MAT raw draws e0..e1 of stream

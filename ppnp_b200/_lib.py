@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("PPNP_B200_LIB") or os.path.join(_HERE, "libppnp_b200.
 # epilogues / modes (keep in sync with include/ppnp_b200.h)
 MODE_SYM, MODE_RW = 0, 1
 EPI_PLAIN, EPI_Z2Y, EPI_Y, EPI_Y2Z, EPI_RW = 0, 1, 2, 3, 4
+EPI_ACC = 16
 FLAG = 0x80000000
 
 
@@ -23,7 +24,7 @@ class PlanStruct(C.Structure):
         ("n", C.c_int64), ("n_edges", C.c_int64), ("n_chunks", C.c_int64), ("n_segs", C.c_int64),
         ("n_fix", C.c_int64), ("n_slots", C.c_int64), ("chunk_edges", C.c_int32), ("reserved", C.c_int32),
         ("cols", C.c_void_p), ("vals", C.c_void_p), ("seg_row", C.c_void_p), ("chunk_seg", C.c_void_p),
-        ("fix_ptr", C.c_void_p), ("fix_row", C.c_void_p), ("fix_deg", C.c_void_p),
+        ("fix_ptr", C.c_void_p), ("fix_row", C.c_void_p), ("fix_deg", C.c_void_p), ("row_deg", C.c_void_p),
     ]
 
 
@@ -50,6 +51,7 @@ SIGNATURES = {
     "ppnp_dense_to_csr": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "ppnp_batch_support": (C.c_int, [_p, _p, _p, _i64, _p, _p]),
     "ppnp_batch_propagate": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _i32, _p]),
+    "ppnp_gather_rows": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _p]),
     "ppnp_rmat_keys": (C.c_int, [_u64, _i32, _i64, _i64, _i64, _p, _p]),
 }
 

@@ -39,13 +39,14 @@ constexpr unsigned FULL = 0xffffffffu;
 // Kept out of line so that the (rarely taken, per segment end) code exists once in the kernel.
 template <int VEC>
 __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t, int sv, float deg, bool active,
-                                          float* __restrict__ Zout, float* __restrict__ partial, int ld, int f,
-                                          float alpha, int epi) {
+                                          float* Zout, float* __restrict__ partial, int ld, int f,
+                                          float alpha, int epi, const float* __restrict__ row_deg) {
     if (!active) return;
     if (sv < 0) {
         acc.store(partial + (int64_t)(sv & 0x7fffffff) * ld + f);
     } else {
         float a, bb;
+        if (row_deg != nullptr) deg = __ldg(row_deg + sv);   // stream holds only part of the row
         epi_coef(epi, alpha, deg, a, bb);
         Vec<VEC>::axpby(a, acc, bb, t).store_stream(Zout + (int64_t)sv * ld + f);
     }
@@ -83,9 +84,9 @@ __global__ void __launch_bounds__(256, (G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOC
 spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
                    const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
                    int64_t n_chunks, int chunk_edges,
-                   const float* __restrict__ Zin, const float* __restrict__ T,
-                   float* __restrict__ Zout, float* __restrict__ partial,
-                   int ld, int F, float alpha, int epi) {
+                   const float* __restrict__ Zin, const float* T,
+                   float* Zout, float* __restrict__ partial,   // T may alias Zout (PPNP_EPI_ACC)
+                   int ld, int F, float alpha, int epi, const float* __restrict__ row_deg) {
     using V = Vec<VEC>;
     using SC = StageCfg<G>;
     constexpr int GPW = 32 / G;                     // groups per warp
@@ -254,7 +255,7 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
                                 const int pos = j * SE + r * G + u0 + u;
                                 {   // copies: the out-of-line call takes references, acc itself must stay in registers
                                     const V a2 = acc, t2 = t[u];
-                                    emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi);
+                                    emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi, row_deg);
                                 }
                                 acc.zero();
                                 seg_begin = pos + 1;
@@ -274,7 +275,7 @@ template <int VEC, int G>
 __global__ void __launch_bounds__(256)
 fixup_kernel(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_row,
              const float* __restrict__ fix_deg, int64_t n_fix, const float* __restrict__ partial,
-             const float* __restrict__ T, float* __restrict__ Zout, int64_t ld, int F, float alpha, int epi) {
+             const float* T, float* Zout, int64_t ld, int F, float alpha, int epi) {
     using V = Vec<VEC>;
     constexpr int GPW = 32 / G;
     constexpr int U = 8;
@@ -336,7 +337,7 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
         const int64_t cap = (int64_t)sm_count() * occ;                                                             \
         dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)tiles);                                           \
         k<<<grid, THREADS, smem_bytes, stream>>>(p->cols, HV_ ? p->vals : nullptr, p->seg_row, p->chunk_seg, p->n_chunks, \
-                                        p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi);            \
+                                        p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi, p->row_deg); \
     } while (0)
     if (use_vals) { if (full_tile) PPNP_LAUNCH(true, true); else PPNP_LAUNCH(true, false); }
     else          { if (full_tile) PPNP_LAUNCH(false, true); else PPNP_LAUNCH(false, false); }
@@ -409,7 +410,8 @@ int ppnp_spmm_step(const ppnp_plan_t* plan, const float* Zin, const float* T, fl
     PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
-    PPNP_REQUIRE(epi >= PPNP_EPI_PLAIN && epi <= PPNP_EPI_RW, "bad epilogue");
+    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~31) == 0, "bad epilogue");
+    PPNP_REQUIRE(!(epi & PPNP_EPI_ACC) || T == Zout, "PPNP_EPI_ACC adds to the output: pass T == Zout");
     return dispatch_step(plan, Zin, T, Zout, partial, ld, F, alpha, epi, use_vals != 0, as_stream(stream));
 }
 

@@ -86,7 +86,7 @@ struct Vec<4> {
 // epilogue coefficients, out = a * acc + b * teleport   (include/ppnp_b200.h PPNP_EPI_*)
 __device__ __forceinline__ void epi_coef(int epi, float alpha, float deg, float& a, float& b) {
     const float oma = 1.0f - alpha;
-    switch (epi) {
+    switch (epi & 15) {
         default:
         case PPNP_EPI_PLAIN: a = oma; b = alpha; break;
         // rsqrtf / __frcp_rn: one MUFU each (<= 2 ulp / correctly rounded); deg is a small integer
@@ -95,6 +95,7 @@ __device__ __forceinline__ void epi_coef(int epi, float alpha, float deg, float&
         case PPNP_EPI_Y2Z: a = oma * rsqrtf(deg); b = alpha; break;
         case PPNP_EPI_RW: a = oma * __frcp_rn(deg); b = alpha; break;
     }
+    if (epi & PPNP_EPI_ACC) b = 1.0f;   // T is the output itself: add to what an earlier pass wrote
 }
 
 }  // namespace ppnp

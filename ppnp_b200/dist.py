@@ -125,57 +125,219 @@ class HaloExchange:
             self._send_buf[key] = buf
         send = buf[: self.send_idx.numel()]
         if self.send_idx.numel():
-            torch.index_select(Zext[: t.n_local], 0, self.send_idx, out=send)
+            if Zext.is_cuda:
+                from .ops import gather_rows
+                gather_rows(Zext[: t.n_local], self.send_idx, send)
+            else:
+                torch.index_select(Zext[: t.n_local], 0, self.send_idx, out=send)
         recv = Zext[t.n_local:]
         return dist.all_to_all_single(recv, send, output_split_sizes=self.recv_counts, input_split_sizes=self.send_counts,
                                       group=self.group, async_op=async_op)
 
 
-# ------------------------------------------------------------------------------ GPU propagation
-class PartitionedPropagation:
-    """K-step APPNP over the shard (CUDA).  Two edge streams: interior rows (overlap the exchange) and
-    boundary rows (after it)."""
+# ------------------------------------------------------------------------------ transports
+class PeerPull:
+    """Halo transport over peer memory: the Z buffers are symmetric-memory allocations, every rank maps
+    its peers' buffers over NVLink and PULLS the rows it needs with one gather kernel per owner
+    (csrc/rows.cu) -- de-duplicated rows, no pack on the sender, no collective; a device-side barrier
+    per step orders the pulls after the owners' writes."""
 
-    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, overlap=True, group=None,
-                 step_fn=None):
+    def __init__(self, topo: ShardTopology, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.topo, self.group = topo, (group if group is not None else dist.group.WORLD)
+        dev = topo.halo_cols.device
+        # ids I want from each owner, local to the owner, and where they land in my halo region
+        self.want, self.offs = [], []
+        o = 0
+        for q in range(topo.world):
+            c = topo.recv_counts[q]
+            self.want.append((topo.halo_cols[o: o + c] - topo.bounds[q]).contiguous())
+            self.offs.append(o)
+            o += c
+        ext = torch.tensor([topo.n_local + topo.n_halo], dtype=torch.int64, device=dev)
+        dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+        self.rows_alloc = int(ext)
+        self.handles = {}
+
+    def alloc(self, F, count=3):
+        """``count`` symmetric [rows_alloc, F] buffers (same size on every rank)."""
+        dev = self.topo.halo_cols.device
+        bufs = []
+        for _ in range(count):
+            t = self.symm_mem.empty((self.rows_alloc, F), dtype=torch.float32, device=dev)
+            h = self.symm_mem.rendezvous(t, self.group)
+            self.handles[t.data_ptr()] = (h, F)
+            bufs.append(t)
+        return bufs
+
+    def step_barrier(self, buf):
+        self.handles[buf.data_ptr()][0].barrier()
+
+    def fetch(self, src, owner):
+        """Pull owner's rows of ``src`` (the same symmetric buffer on every rank) into my halo region."""
+        from .ops import gather_rows
+        t = self.topo
+        c = t.recv_counts[owner]
+        if c == 0:
+            return
+        h, F = self.handles[src.data_ptr()]
+        n_owner = t.bounds[owner + 1] - t.bounds[owner]
+        peer = h.get_buffer(owner, (n_owner, F), torch.float32)
+        gather_rows(peer, self.want[owner], src[t.n_local + self.offs[owner]: t.n_local + self.offs[owner] + c])
+
+
+class RoundSendRecv:
+    """Halo transport over torch.distributed point-to-point (NCCL on GPUs, gloo in the CPU tests): the
+    rows a peer needs are packed (csrc/rows.cu on CUDA) and sent, its rows for me are received straight
+    into their halo slots."""
+
+    def __init__(self, topo: ShardTopology, group=None):
+        self.hx = HaloExchange(topo, group)
+        self.topo, self.group = topo, group
+        self.soffs, o = [], 0
+        for q in range(topo.world):
+            self.soffs.append(o)
+            o += self.hx.send_counts[q]
+        self.roffs, o = [], 0
+        for q in range(topo.world):
+            self.roffs.append(o)
+            o += topo.recv_counts[q]
+        self._buf = {}
+
+    def alloc(self, F, count=3):
+        dev = self.topo.halo_cols.device
+        return [torch.zeros((self.topo.n_local + self.topo.n_halo, F), dtype=torch.float32, device=dev) for _ in range(count)]
+
+    def step_barrier(self, buf):
+        pass
+
+    def exchange_round(self, src, dest, source):
+        """Send my rows that ``dest`` needs, receive ``source``'s rows that I need."""
+        t = self.topo
+        F = src.shape[1]
+        ops = []
+        ns, nr = self.hx.send_counts[dest], t.recv_counts[source]
+        if ns:
+            key = (F, dest)
+            buf = self._buf.get(key)
+            if buf is None:
+                buf = torch.empty((ns, F), dtype=torch.float32, device=src.device)
+                self._buf[key] = buf
+            ids = self.hx.send_idx[self.soffs[dest]: self.soffs[dest] + ns]
+            if src.is_cuda:
+                from .ops import gather_rows
+                gather_rows(src[: t.n_local], ids, buf)
+            else:
+                torch.index_select(src[: t.n_local], 0, ids, out=buf)
+            ops.append(dist.P2POp(dist.isend, buf, dest, self.group))
+        if nr:
+            ops.append(dist.P2POp(dist.irecv, src[t.n_local + self.roffs[source]: t.n_local + self.roffs[source] + nr], source, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+
+# ------------------------------------------------------------------------------ propagation
+class PartitionedPropagation:
+    """K-step APPNP over one shard.
+
+    A step is split into PHASES by where an edge's column lives: phase 0 = columns owned by this
+    rank (every row has its self loop there, so phase 0 writes every output row, teleport term
+    included); phase t >= 1 = columns owned by rank (rank - t) mod P, ADDED to the rows phase 0 wrote
+    (PPNP_EPI_ACC).  Transfers run on a side stream in the same order, so the rows of owner t+1 are in
+    flight while the edges that point at owner t are processed -- the exchange hides behind the
+    compute edge by edge, not just behind the few rows without remote neighbours.
+    ``phases``: "peer" (one phase per owner), "two" (local, then all remote), "one" (no split)."""
+
+    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, phases="peer", transport="auto",
+                 group=None, step_fn=None):
         """``step_fn(plan, Zin, T, Zout, alpha, epi, use_vals)`` replaces the CUDA launch; it exists so
         that tests can drive this orchestration on CPU tensors (gloo) with a numpy walker of the
         plan.  The package itself ships no CPU implementation: the default is the CUDA library."""
-        self.topo = topo
-        self._step_fn = step_fn
-        self.overlap = overlap
-        self.exchange = HaloExchange(topo, group)
+        from .plan import build_stream_plan
+        self.topo, self._step_fn, self.phases = topo, step_fn, phases
         dev = topo.indices.device
+        self.on_gpu = dev.type == "cuda"
+        if transport == "auto":
+            transport = "pull" if self.on_gpu else "p2p"
+        self.transport_name = transport
+        self.transport = PeerPull(topo, group) if transport == "pull" else RoundSendRecv(topo, group)
+        P, rank, n_local = topo.world, topo.rank, topo.n_local
         ip = topo.indptr
-        deg = (ip[1:] - ip[:-1])
-        lo = topo.bounds[topo.rank]
+        deg = ip[1:] - ip[:-1]
+        lo = topo.bounds[rank]
         # stored values of the first step: dinv_i * dinv_j with GLOBAL degrees
-        dinv_ext = torch.cat([deg_global_dinv[lo: lo + topo.n_local], deg_global_dinv[topo.halo_cols]])
-        row_of = torch.repeat_interleave(torch.arange(topo.n_local, device=dev), deg)
-        vals = dinv_ext[row_of] * dinv_ext[topo.indices.to(torch.int64)]
-        del row_of
-        order_int = torch.nonzero(topo.interior).flatten()
-        order_bnd = torch.nonzero(~topo.interior).flatten()
+        dinv_ext = torch.cat([deg_global_dinv[lo: lo + n_local], deg_global_dinv[topo.halo_cols]])
+        row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), deg)
+        cols = topo.indices.to(torch.int64)
+        vals = dinv_ext[row_of] * dinv_ext[cols]
+        # phase of every edge
+        b = torch.tensor(topo.bounds, dtype=torch.int64, device=dev)
+        halo_owner = torch.searchsorted(b, topo.halo_cols, right=True) - 1
+        if phases == "one" or P == 1:
+            self.rounds = []                              # (phase id, owner) pairs after phase 0
+            edge_phase = torch.zeros_like(cols)
+            n_ph = 1
+        else:
+            if phases == "two":
+                owner_phase = torch.ones(P, dtype=torch.int64, device=dev)
+                self.rounds = [(1, None)]
+                n_ph = 2
+            else:
+                owner_phase = (rank - torch.arange(P, device=dev)) % P       # owner q arrives in round (rank - q) mod P
+                self.rounds = [(t, (rank - t) % P) for t in range(1, P)]
+                n_ph = P
+            ext_phase = torch.cat([torch.zeros(n_local, dtype=torch.int64, device=dev), owner_phase[halo_owner]])
+            edge_phase = ext_phase[cols]
         self.plans = []
-        for rows in ((order_int, order_bnd) if overlap else (torch.arange(topo.n_local, device=dev),)):
+        deg_f = deg.to(torch.float32)
+        for ph in range(n_ph):
+            m = edge_phase == ph
+            cnt = torch.bincount(row_of[m], minlength=n_local)
+            rows = torch.nonzero(cnt).flatten()
             if rows.numel() == 0:
                 self.plans.append(None)
                 continue
-            d = deg[rows]
-            order = rows[torch.sort(d, descending=True, stable=True).indices]
-            self.plans.append(_SubGraph(build_stream_plan_subset(ip, topo.indices, vals, chunk_edges, order, topo.n_local), step_fn))
-        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+            ipp = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
+            ipp[1:] = torch.cumsum(cnt, 0)
+            order = rows[torch.sort(cnt[rows], descending=True, stable=True).indices]
+            plan = build_stream_plan(ipp, topo.indices[m], vals[m], chunk_edges, order, subset=True,
+                                     row_deg=(deg_f if n_ph > 1 else None))
+            self.plans.append(_SubGraph(plan, step_fn))
+            del m, cnt, ipp
+        del row_of, cols, vals, edge_phase
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.on_gpu else None
+        self.exchange = self.transport.hx if isinstance(self.transport, RoundSendRecv) else None
 
     def n_ext(self):
         return self.topo.n_local + self.topo.n_halo
 
+    def alloc(self, F):
+        """H, Z, S buffers of [>= n_local + n_halo, F] usable with this transport."""
+        return self.transport.alloc(F, 3)
+
+    def _transfer(self, src, rnd):
+        ph, owner = rnd
+        t = self.topo
+        if owner is None:                                  # all owners at once
+            if isinstance(self.transport, PeerPull):
+                for q in range(t.world):
+                    if q != t.rank:
+                        self.transport.fetch(src, q)
+            else:
+                self.transport.hx.exchange(src[: t.n_local + t.n_halo])
+        elif isinstance(self.transport, PeerPull):
+            self.transport.fetch(src, owner)
+        else:
+            self.transport.exchange_round(src, dest=(t.rank + ph) % t.world, source=owner)
+
     def propagate(self, H_ext, Z_ext, S_ext, K, alpha):
-        """H_ext/Z_ext/S_ext: [n_local + n_halo, F] buffers; H_ext[:n_local] holds the input.  Result in
-        Z_ext[:n_local].  Value-free Y-space iteration as on one GPU (epilogues PPNP_EPI_*)."""
+        """H_ext[:n_local] holds the input; result in Z_ext[:n_local].  Value-free Y-space iteration as on
+        one GPU (epilogues PPNP_EPI_*)."""
         from . import _lib
         t = self.topo
-        on_gpu = self.comm_stream is not None
-        cur = torch.cuda.current_stream() if on_gpu else None
+        cur = torch.cuda.current_stream() if self.on_gpu else None
         src = H_ext
         for k in range(1, K + 1):
             dst = Z_ext if (K - k) % 2 == 0 else S_ext
@@ -187,35 +349,33 @@ class PartitionedPropagation:
                 epi, use_vals = _lib.EPI_Y2Z, False
             else:
                 epi, use_vals = _lib.EPI_Y, False
-            if self.overlap and on_gpu:
-                self.comm_stream.wait_stream(cur)
-                with torch.cuda.stream(self.comm_stream):
-                    self.exchange.exchange(src)
-                if self.plans[0] is not None:
-                    self.plans[0].step(src, H_ext, dst, alpha, epi, use_vals)
-                cur.wait_stream(self.comm_stream)
-                if self.plans[1] is not None:
-                    self.plans[1].step(src, H_ext, dst, alpha, epi, use_vals)
-            elif self.overlap:
-                work = self.exchange.exchange(src, async_op=True)
-                if self.plans[0] is not None:
-                    self.plans[0].step(src, H_ext, dst, alpha, epi, use_vals)
-                if work is not None:
-                    work.wait()
-                if self.plans[1] is not None:
-                    self.plans[1].step(src, H_ext, dst, alpha, epi, use_vals)
-            else:
-                self.exchange.exchange(src)
+            self.transport.step_barrier(src)               # every rank has finished writing `src` (and reading `dst`)
+            if not self.rounds:                            # single phase: full exchange, then everything
+                if t.world > 1:
+                    self._transfer(src, (1, None))
                 self.plans[0].step(src, H_ext, dst, alpha, epi, use_vals)
+            elif self.on_gpu:
+                self.comm_stream.wait_stream(cur)
+                events = []
+                with torch.cuda.stream(self.comm_stream):
+                    for rnd in self.rounds:
+                        self._transfer(src, rnd)
+                        ev = torch.cuda.Event()
+                        ev.record(self.comm_stream)
+                        events.append(ev)
+                self.plans[0].step(src, H_ext, dst, alpha, epi, use_vals)
+                for rnd, ev in zip(self.rounds, events):
+                    cur.wait_event(ev)
+                    if self.plans[rnd[0]] is not None:
+                        self.plans[rnd[0]].step(src, dst, dst, alpha, epi | _lib.EPI_ACC, use_vals)
+            else:
+                self.plans[0].step(src, H_ext, dst, alpha, epi, use_vals)
+                for rnd in self.rounds:
+                    self._transfer(src, rnd)
+                    if self.plans[rnd[0]] is not None:
+                        self.plans[rnd[0]].step(src, dst, dst, alpha, epi | _lib.EPI_ACC, use_vals)
             src = dst
         return Z_ext[: t.n_local]
-
-
-def build_stream_plan_subset(indptr, indices, vals, chunk_edges, order, n_rows_total):
-    """Edge stream over a subset of rows (``order``): the plan builder takes any row order; rows that
-    are left out simply never appear."""
-    from .plan import build_stream_plan
-    return build_stream_plan(indptr, indices, vals, chunk_edges, order, subset=True)
 
 
 class _SubGraph:
@@ -311,7 +471,7 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
     return 1.0 / torch.sqrt(out)
 
 
-def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, overlap=True):
+def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto"):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
@@ -320,17 +480,16 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
-    prop = PartitionedPropagation(topo, dinv, overlap=overlap)
+    prop = PartitionedPropagation(topo, dinv, phases=phases, transport=transport)
     del dinv
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
-    n_ext = prop.n_ext()
+    H, G, Z, S = prop.transport.alloc(F, 4)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
-    H = torch.zeros(n_ext, F, device=dev)
-    G = torch.zeros(n_ext, F, device=dev)
+    for b in (H, G, Z, S):
+        b.zero_()
     H[: topo.n_local].normal_(generator=g)
     G[: topo.n_local].normal_(generator=g)
-    Z, S = torch.empty_like(H), torch.empty_like(H)
 
     def one_pass():
         prop.propagate(H, Z, S, K, alpha)
@@ -375,8 +534,8 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     ms_e2e = torch.tensor([e0.elapsed_time(e1) / 2], device=dev)
     dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
 
-    # diagnostics: the exchange alone and the compute alone (not part of the headline number)
-    def timed(fn, reps=5):
+    # diagnostics: the transfers alone and the compute alone (not part of the headline number)
+    def timed(fn, reps=4):
         torch.cuda.synchronize(); dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -388,16 +547,22 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         return float(t)
 
     from . import _lib as _l
-    ms_exchange = timed(lambda: prop.exchange.exchange(Z))
+
+    def transfers_only():
+        prop.transport.step_barrier(Z)
+        for rnd in (prop.rounds or ([(1, None)] if world > 1 else [])):
+            prop._transfer(Z, rnd)
+    ms_exchange = timed(transfers_only)
 
     def compute_only():
+        first = True
         for p in prop.plans:
             if p is not None:
-                p.step(Z, H, S, alpha, _l.EPI_Y, False)
+                p.step(Z, H if first else S, S, alpha, _l.EPI_Y | (0 if first else _l.EPI_ACC), False)
+            first = False
     ms_compute = timed(compute_only)
 
-    stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum()),
-                          sum(prop.exchange.send_counts)], dtype=torch.int64, device=dev)
+    stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum())], dtype=torch.int64, device=dev)
     allstats = [torch.empty_like(stats) for _ in range(world)]
     dist.all_gather(allstats, stats)
     nnz = int(sum(int(s[0]) for s in allstats))
@@ -405,16 +570,17 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     for p in prop.plans:
         if p is not None:
             launches += 2 if p.plan.n_fix > 0 else 1
+    launches += len(prop.rounds) if prop.transport_name == "pull" else 0
     work = 2 * K * nnz * F
     return {
         "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,
-        "partition": {"rule": "contiguous row blocks cut at the non-zero prefix sum", "overlap": bool(overlap),
+        "partition": {"rule": "contiguous row blocks cut at the non-zero prefix sum", "phases": phases,
+                      "transport": prop.transport_name,
                       "rows": [int(s[2]) for s in allstats], "nnz": [int(s[0]) for s in allstats],
-                      "halo_rows": [int(s[1]) for s in allstats], "interior_rows": [int(s[3]) for s in allstats],
-                      "sent_rows_per_step": [int(s[4]) for s in allstats]},
+                      "halo_rows": [int(s[1]) for s in allstats], "interior_rows": [int(s[3]) for s in allstats]},
         "e2e": {"value": work / (float(ms_e2e) * 1e-3), "unit": "edge*feature/s", "ms_per_step": float(ms_e2e),
                 "h2d_bytes_per_step": 2 * n * F * 4, "d2h_bytes_per_step": 2 * n * F * 4},
         "gpu_launches": launches * 2 * K * steps, "graph_build_s": round(t_build, 1),
-        "halo_bytes_per_step_rank0": prop.exchange.bytes_per_step(F),
-        "exchange_ms_alone": ms_exchange, "spmm_step_ms_alone": ms_compute,
+        "halo_bytes_received_per_step_rank0": topo.n_halo * F * 4,
+        "transfers_ms_alone": ms_exchange, "spmm_step_ms_alone": ms_compute,
     }

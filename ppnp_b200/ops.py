@@ -406,3 +406,20 @@ def batch_propagate(sp_ppr: SparsePPR, idx_batch, sel, Hsub):
     idx_batch = idx_batch.to(device=dev, dtype=torch.int64).contiguous()
     colmap = (torch.cumsum(sel.to(torch.int32), 0, dtype=torch.int32) - 1).contiguous()
     return _BatchPropagateFunction.apply(Hsub, sp_ppr, idx_batch, colmap)
+
+
+# ------------------------------------------------------------------------------ partitioned helper
+def gather_rows(src, idx, out):
+    """out[i] = src[idx[i]] (fp32 rows); ``src`` may be a peer GPU's symmetric-memory view."""
+    lib = _lib.load()
+    _require_cuda(src, idx, out)
+    n_rows = idx.numel()
+    if n_rows == 0:
+        return out
+    if src.stride(1) != 1 or out.stride(1) != 1 or idx.dtype != torch.int64:
+        raise ValueError("gather_rows needs row-major fp32 matrices and an int64 index")
+    with torch.cuda.device(out.device):
+        rc = lib.ppnp_gather_rows(_lib.ptr(src), src.stride(0), _lib.ptr(idx), n_rows, src.shape[1], _lib.ptr(out),
+                                  out.stride(0), _lib.current_stream())
+    _lib.check(rc, "ppnp_gather_rows")
+    return out

@@ -37,6 +37,7 @@ class StreamPlan:
     n_slots: int
     order: Optional[torch.Tensor] = None   # processing order of the rows (None = natural)
     n_segs_real: int = 0
+    row_deg: Optional[torch.Tensor] = None  # fp32 [n]: full row degrees for partial-row streams
     _struct: object = field(default=None, repr=False)
 
     @property
@@ -65,6 +66,7 @@ class StreamPlan:
             s.fix_ptr = self.fix_ptr.data_ptr()
             s.fix_row = self.fix_row.data_ptr() if self.n_fix else None
             s.fix_deg = self.fix_deg.data_ptr() if self.n_fix else None
+            s.row_deg = self.row_deg.data_ptr() if self.row_deg is not None else None
             self._struct = s
         return self._struct
 
@@ -77,10 +79,10 @@ class StreamPlan:
         mv = lambda t: None if t is None else t.to(device)
         return StreamPlan(self.n, self.nnz, self.chunk_edges, self.n_chunks, mv(self.cols), mv(self.vals),
                           mv(self.seg_row), mv(self.chunk_seg), mv(self.fix_ptr), mv(self.fix_row),
-                          mv(self.fix_deg), self.n_slots, mv(self.order), self.n_segs_real)
+                          mv(self.fix_deg), self.n_slots, mv(self.order), self.n_segs_real, mv(self.row_deg))
 
 
-def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None, subset=False):
+def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None, subset=False, row_deg=None):
     """Cut the CSR (indptr[n+1], indices[nnz], optional vals[nnz]) into the edge stream.
 
     ``order`` (int64, a permutation of the rows) is the processing order; column ids are never
@@ -98,8 +100,9 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None, s
         raise ValueError("indptr[-1] != len(indices)")
     W = chunk_edges
     deg = ip[1:] - ip[:-1]
-    if bool((deg <= 0).any()):
-        raise ValueError("every row of A_hat needs at least its self loop")
+    listed = deg if (order is None or not subset) else deg[order.to(device=dev, dtype=torch.int64)]
+    if bool((listed <= 0).any()):
+        raise ValueError("every streamed row needs at least one edge (A_hat rows hold their self loop)")
 
     n_rows_total = n
     if order is None:
@@ -172,9 +175,12 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None, s
     if fix_rows_pos.numel():
         fp[1:] = torch.cumsum(pieces[fix_rows_pos], 0)
     fix_deg = L[fix_rows_pos].to(torch.float32)
+    if row_deg is not None:   # partial-row stream: the epilogue needs the degree of the whole row
+        row_deg = row_deg.to(device=dev, dtype=torch.float32).contiguous()
+        fix_deg = row_deg[fix_row.to(torch.int64)]
     return StreamPlan(n=n_rows_total, nnz=nnz, chunk_edges=W, n_chunks=n_chunks, cols=cols, vals=svals, seg_row=seg_row,
                       chunk_seg=chunk_seg, fix_ptr=fp.to(torch.int32), fix_row=fix_row, fix_deg=fix_deg,
-                      n_slots=n_slots, order=order, n_segs_real=n_real_segs)
+                      n_slots=n_slots, order=order, n_segs_real=n_real_segs, row_deg=row_deg)
 
 
 def degree_order(indptr):

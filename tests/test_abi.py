@@ -40,8 +40,8 @@ def test_binding_table_matches_header():
 
 def test_plan_struct_layout_matches_header():
     from ppnp_b200 import _lib
-    # 6 x int64, 2 x int32, 7 pointers
-    assert ctypes.sizeof(_lib.PlanStruct) == 6 * 8 + 2 * 4 + 7 * 8
+    # 6 x int64, 2 x int32, 8 pointers
+    assert ctypes.sizeof(_lib.PlanStruct) == 6 * 8 + 2 * 4 + 8 * 8
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -19,7 +19,10 @@ def walker_step(plan, Zin, T, Zout, alpha, epi, use_vals):
     """numpy stand-in for ppnp_spmm_step over a (subset) plan: writes only the rows the plan produces."""
     cols = plan.cols.numpy(); vals = plan.vals.numpy() if plan.vals is not None else None
     seg_row = plan.seg_row.numpy(); chunk_seg = plan.chunk_seg.numpy(); W = plan.chunk_edges
-    Zi = Zin.numpy().astype(np.float64); Tn = T.numpy().astype(np.float64)
+    Zi = Zin.numpy().astype(np.float64); Tn = T.numpy().astype(np.float64).copy()   # T may be Zout (EPI_ACC)
+    rd = plan.row_deg.numpy() if plan.row_deg is not None else None
+    acc_mode = bool(epi & 16)
+    epi &= 15
     F = Zi.shape[1]
     partial = np.zeros((max(plan.n_slots, 1), F))
     for c in range(plan.n_chunks):
@@ -32,16 +35,18 @@ def walker_step(plan, Zin, T, Zout, alpha, epi, use_vals):
                 if sv < 0:
                     partial[sv & 0x7FFFFFFF] = acc
                 else:
-                    a, b = epi_coef(epi, alpha, cnt)
+                    a, b = epi_coef(epi, alpha, cnt if rd is None else float(rd[sv]))
+                    b = 1.0 if acc_mode else b
                     Zout[sv] = torch.from_numpy((a * acc + b * Tn[sv]).astype(np.float32))
                 acc = np.zeros(F); cnt = 0
     fp, fr, fd = plan.fix_ptr.numpy(), plan.fix_row.numpy(), plan.fix_deg.numpy()
     for q in range(plan.n_fix):
         a, b = epi_coef(epi, alpha, float(fd[q]))
+        b = 1.0 if acc_mode else b
         Zout[fr[q]] = torch.from_numpy((a * partial[fp[q]:fp[q + 1]].sum(0) + b * Tn[fr[q]]).astype(np.float32))
 
 
-def worker(rank, world, port, overlap, outdir):
+def worker(rank, world, port, phases, outdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -65,7 +70,7 @@ def worker(rank, world, port, overlap, outdir):
         assert sum(topo.recv_counts) == topo.n_halo
         dinv = pd.global_dinv(ipl, bounds, rank, world, torch.device("cpu"))
         assert np.allclose(dinv.numpy(), 1 / np.sqrt(odeg))
-        prop = pd.PartitionedPropagation(topo, dinv, chunk_edges=128, overlap=overlap, step_fn=walker_step)
+        prop = pd.PartitionedPropagation(topo, dinv, chunk_edges=128, phases=phases, step_fn=walker_step)
         rng = np.random.RandomState(0)
         Hg = rng.randn(n, F).astype(np.float32)                                # the same global H on every rank
         n_ext = prop.n_ext()
@@ -86,10 +91,10 @@ def worker(rank, world, port, overlap, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,overlap", [(2, True), (2, False), (3, True)])
-def test_partitioned_propagation_gloo(tmp_path, world, overlap):
-    port = 29600 + world * 10 + int(overlap) + (os.getpid() % 50)
-    mp.spawn(worker, args=(world, port, overlap, str(tmp_path)), nprocs=world, join=True)
+@pytest.mark.parametrize("world,phases", [(2, "peer"), (2, "one"), (3, "peer"), (3, "two")])
+def test_partitioned_propagation_gloo(tmp_path, world, phases):
+    port = 29600 + world * 10 + len(phases) + (os.getpid() % 50)
+    mp.spawn(worker, args=(world, port, phases, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok_{r}") for r in range(world))
 
 

@@ -13,7 +13,7 @@ from util import oracle, relerr
 pytestmark = pytest.mark.gpu
 
 
-def worker(rank, world, port, overlap, outdir):
+def worker(rank, world, port, mode, outdir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -25,12 +25,13 @@ def worker(rank, world, port, overlap, outdir):
         indptr, cols, bounds = pd.rmat_shard(n, raw, scale, 0, dev, rank, world, batch=1 << 20)
         dinv = pd.global_dinv(indptr, bounds, rank, world, dev)
         topo = pd.build_shard_topology(indptr, cols, bounds, rank)
-        prop = pd.PartitionedPropagation(topo, dinv, overlap=overlap)
+        phases, transport = mode.split("/")
+        prop = pd.PartitionedPropagation(topo, dinv, phases=phases, transport=transport)
         lo, hi = bounds[rank], bounds[rank + 1]
         Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
-        H = torch.zeros(prop.n_ext(), F, device=dev)
+        H, Z, S = prop.transport.alloc(F, 3)
+        H.zero_()
         H[: topo.n_local] = torch.from_numpy(Hg[lo:hi]).to(dev)
-        Z, S = torch.empty_like(H), torch.empty_like(H)
         out = prop.propagate(H, Z, S, K, alpha).cpu().numpy()
         # oracle on the host: the same recipe through the C generator
         ip, idx = oracle.rmat_graph(n, raw, scale, seed=0)
@@ -45,10 +46,10 @@ def worker(rank, world, port, overlap, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [False, True])
-def test_partitioned_matches_oracle_on_two_gpus(tmp_path, overlap):
+@pytest.mark.parametrize("mode", ["peer/pull", "peer/p2p", "two/pull", "one/p2p"])
+def test_partitioned_matches_oracle_on_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    port = 29700 + int(overlap) + (os.getpid() % 50)
-    mp.spawn(worker, args=(2, port, overlap, str(tmp_path)), nprocs=2, join=True)
+    port = 29700 + len(mode) + (hash(mode) % 40) + (os.getpid() % 50)
+    mp.spawn(worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"ok_{r}") for r in range(2))
