@@ -187,22 +187,28 @@ def run_ours(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    wl = args.workload or ("rmat2m" if world == 1 else "rmat100m")
+    # config 5 family: always through the partitioned code path, also at N=1, so that T_1 and T_P of the
+    # scaling study come from the same code
+    partitioned = world > 1 or wl in ("rmat100m", "rmat16m")
+    if partitioned:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        os.environ.setdefault("RANK", "0")
+        os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=dev)
     __import__("__graft_entry__").build() if rank == 0 else None
-    if world > 1:
+    if partitioned:
         dist.barrier()
     import ppnp_b200 as P
     from ppnp_b200.synth import rmat_adjacency
 
-    wl = args.workload or ("rmat2m" if world == 1 else "rmat100m")
     n, raw, scale, F = WORKLOADS[wl]
     steps = args.steps if args.steps is not None else 10
     warmup = args.warmup if args.warmup is not None else 3
     peak, peak_src = measured_peaks()
 
-    if world > 1:
+    if partitioned:
         from ppnp_b200 import dist as pd
         result = pd.bench_partitioned(wl, n, raw, scale, F, KSTEPS, ALPHA, steps, warmup, dev, rank, world,
                                        phases=args.phases, transport=args.transport)
@@ -215,7 +221,7 @@ def run_ours(args):
             bytes_pass = algorithmic_bytes_per_pass(n, nnz, F)
             line = {
                 "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": wl, "n": n, "nnz_a_hat": nnz, "F": F, "K": KSTEPS, "alpha": ALPHA,
                            "pass": "K=10 forward + K=10 backward", "partition": result.pop("partition"),

@@ -122,6 +122,13 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
                          float* partial, int64_t ld, int32_t F, int32_t K, float alpha,
                          int32_t mode, int32_t use_vals, void* stream);
 
+/* The same K steps in ONE cooperative launch (grid-wide barriers between the steps; stored-value
+ * form).  ppnp_appnp_propagate takes this path by itself for small graphs (<= 4096 chunks) unless
+ * PPNP_PERSISTENT=0 is set in the environment. */
+int ppnp_appnp_propagate_persistent(const ppnp_plan_t* plan, const float* H, float* Z, float* scratch,
+                                    float* partial, int64_t ld, int32_t F, int32_t K, float alpha,
+                                    void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (3) Exact PPNP.                                      replaces helpers.py:68-71 compute_ppr
  *     Pi = alpha (I - (1-alpha) A_hat)^-1 by power iteration on all n right-hand sides:

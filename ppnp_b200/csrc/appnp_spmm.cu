@@ -14,6 +14,9 @@
 //     fixup_kernel adds up in slot order (deterministic, no atomics),
 //   * column indices, teleport rows and outputs are streamed with evict-first hints so that
 //     the gathered Z rows (re-used across hub neighbourhoods) keep the 126 MB L2.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ppnp {
@@ -24,6 +27,9 @@ constexpr unsigned FULL = 0xffffffffu;
 // tuning knobs (overridable at build time for experiments, see tools/)
 #ifndef PPNP_SPMM_MINBLOCKS
 #define PPNP_SPMM_MINBLOCKS 4   // resident 256-thread CTAs per SM the register budget is capped for
+#endif
+#ifndef PPNP_PERSISTENT_MAX_CHUNKS
+#define PPNP_PERSISTENT_MAX_CHUNKS 4096   // <= 1 M edges: launch latency dominates, use the one-launch K-step kernel
 #endif
 #ifndef PPNP_SPMM_MINBLOCKS_WIDE
 #define PPNP_SPMM_MINBLOCKS_WIDE 3   // same, for the variants that carry several index registers or values
@@ -37,6 +43,12 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // Finish a segment: either park the partial sum or apply the epilogue and stream the row out.
 // Kept out of line so that the (rarely taken, per segment end) code exists once in the kernel.
+template <typename V, bool COHERENT>
+__device__ __forceinline__ V gather_load(const float* p) {
+    if (COHERENT) return V::load_cg(p);
+    return V::load(p);
+}
+
 template <int VEC>
 __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t, int sv, float deg, bool active,
                                           float* Zout, float* __restrict__ partial, int ld, int f,
@@ -79,14 +91,16 @@ struct StageCfg {
     static constexpr int words_per_thread(bool has_val) { return SR * (ISLOTS * (has_val ? 2 : 1) + SSLOTS); }
 };
 
-template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE>
-__global__ void __launch_bounds__(256, (G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOCKS : PPNP_SPMM_MINBLOCKS_WIDE)
-spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
-                   const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
-                   int64_t n_chunks, int chunk_edges,
-                   const float* __restrict__ Zin, const float* T,
-                   float* Zout, float* __restrict__ partial,   // T may alias Zout (PPNP_EPI_ACC)
-                   int ld, int F, float alpha, int epi, const float* __restrict__ row_deg) {
+// COHERENT: gathers bypass L1 (ld.global.cg).  Needed when the source was written earlier in the SAME
+// launch (persistent K-step kernel): ld.global.nc / L1 hits could return the previous iterate.
+template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE, bool COHERENT>
+__device__ __forceinline__ void
+spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ vals,
+                 const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
+                 int64_t n_chunks, int chunk_edges,
+                 const float* Zin, const float* T,
+                 float* Zout, float* partial,   // T may alias Zout (PPNP_EPI_ACC)
+                 int ld, int F, float alpha, int epi, const float* __restrict__ row_deg) {
     using V = Vec<VEC>;
     using SC = StageCfg<G>;
     constexpr int GPW = 32 / G;                     // groups per warp
@@ -204,14 +218,14 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
                     const int col = __shfl_sync(FULL, raw0[e / G], e % G, G);
                     if (HAS_VAL) wv[e] = __shfl_sync(FULL, w0[e / G], e % G, G);
                     v[e].zero();
-                    if (active) v[e] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                    if (active) v[e] = gather_load<V, COHERENT>(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
                 }
 #pragma unroll
                 for (int e = RING; e < SE; ++e) {
                     if (HAS_VAL) acc.fma(wv[e % RING], v[e % RING]); else acc.add(v[e % RING]);
                     const int col = __shfl_sync(FULL, raw0[e / G], e % G, G);
                     if (HAS_VAL) wv[e % RING] = __shfl_sync(FULL, w0[e / G], e % G, G);
-                    if (active) v[e % RING] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                    if (active) v[e % RING] = gather_load<V, COHERENT>(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
                 }
 #pragma unroll
                 for (int e = 0; e < RING; ++e) {
@@ -229,7 +243,7 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
                         for (int u = 0; u < U; ++u) {
                             const int col = __shfl_sync(FULL, raw0[r], u0 + u, G);
                             v[u].zero();
-                            if (active) v[u] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                            if (active) v[u] = gather_load<V, COHERENT>(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
                         }
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
@@ -245,7 +259,7 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
                             sv[u] = __shfl_sync(FULL, segv0[r], u0 + u, G);
                             v[u].zero();
                             t[u].zero();
-                            if (active) v[u] = V::load(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)(ru[u] & 0x7fffffff) * row_bytes));
+                            if (active) v[u] = gather_load<V, COHERENT>(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)(ru[u] & 0x7fffffff) * row_bytes));
                             if (active && ru[u] < 0 && sv[u] >= 0) t[u] = V::load_stream(reinterpret_cast<const float*>(tbase + (uint64_t)(unsigned)sv[u] * row_bytes));
                         }
 #pragma unroll
@@ -270,12 +284,22 @@ spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ v
     }
 }
 
+template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE>
+__global__ void __launch_bounds__(256, (G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOCKS : PPNP_SPMM_MINBLOCKS_WIDE)
+spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
+                   const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
+                   int64_t n_chunks, int chunk_edges, const float* Zin, const float* T, float* Zout,
+                   float* partial, int ld, int F, float alpha, int epi, const float* __restrict__ row_deg) {
+    spmm_stream_body<VEC, G, HAS_VAL, U, FULL_TILE, false>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, Zin, T,
+                                                           Zout, partial, ld, F, alpha, epi, row_deg);
+}
+
 // Rows split over several segments: add the partial sums in slot order, then the epilogue.
-template <int VEC, int G>
-__global__ void __launch_bounds__(256)
-fixup_kernel(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_row,
-             const float* __restrict__ fix_deg, int64_t n_fix, const float* __restrict__ partial,
-             const float* T, float* Zout, int64_t ld, int F, float alpha, int epi) {
+template <int VEC, int G, bool COHERENT>
+__device__ __forceinline__ void
+fixup_body(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_row,
+           const float* __restrict__ fix_deg, int64_t n_fix, const float* partial,
+           const float* T, float* Zout, int64_t ld, int F, float alpha, int epi) {
     using V = Vec<VEC>;
     constexpr int GPW = 32 / G;
     constexpr int U = 8;
@@ -285,24 +309,60 @@ fixup_kernel(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fi
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t total_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * GPW;
     const int f = ((int)blockIdx.y * G + lg) * VEC;
-    if (f >= F) return;
-    for (int64_t q = warp_global * GPW + g; q < n_fix; q += total_groups) {
-        const int s0 = __ldg(fix_ptr + q), s1 = __ldg(fix_ptr + q + 1);
-        const int row = __ldg(fix_row + q);
-        const V t = V::load_stream(T + (int64_t)row * ld + f);
-        V acc; acc.zero();
-        int s = s0;
-        for (; s + U <= s1; s += U) {
-            V p[U];
+    if (f < F) {
+        for (int64_t q = warp_global * GPW + g; q < n_fix; q += total_groups) {
+            const int s0 = __ldg(fix_ptr + q), s1 = __ldg(fix_ptr + q + 1);
+            const int row = __ldg(fix_row + q);
+            const V t = V::load_stream(T + (int64_t)row * ld + f);
+            V acc; acc.zero();
+            int s = s0;
+            for (; s + U <= s1; s += U) {
+                V p[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) p[u] = V::load_plain(partial + (int64_t)(s + u) * ld + f);
+                for (int u = 0; u < U; ++u) p[u] = COHERENT ? V::load_cg(partial + (int64_t)(s + u) * ld + f) : V::load_plain(partial + (int64_t)(s + u) * ld + f);
 #pragma unroll
-            for (int u = 0; u < U; ++u) acc.add(p[u]);
+                for (int u = 0; u < U; ++u) acc.add(p[u]);
+            }
+            for (; s < s1; ++s) acc.add(COHERENT ? V::load_cg(partial + (int64_t)s * ld + f) : V::load_plain(partial + (int64_t)s * ld + f));
+            float a, bb;
+            epi_coef(epi, alpha, __ldg(fix_deg + q), a, bb);
+            V::axpby(a, acc, bb, t).store_stream(Zout + (int64_t)row * ld + f);
         }
-        for (; s < s1; ++s) acc.add(V::load_plain(partial + (int64_t)s * ld + f));
-        float a, bb;
-        epi_coef(epi, alpha, __ldg(fix_deg + q), a, bb);
-        V::axpby(a, acc, bb, t).store_stream(Zout + (int64_t)row * ld + f);
+    }
+}
+
+template <int VEC, int G>
+__global__ void __launch_bounds__(256)
+fixup_kernel(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_row,
+             const float* __restrict__ fix_deg, int64_t n_fix, const float* __restrict__ partial,
+             const float* T, float* Zout, int64_t ld, int F, float alpha, int epi) {
+    fixup_body<VEC, G, false>(fix_ptr, fix_row, fix_deg, n_fix, partial, T, Zout, ld, F, alpha, epi);
+}
+
+// All K steps in ONE cooperative launch (north_star: "all K iterations in one persistent launch where
+// the graph fits"): grid-wide barriers replace 2K kernel launches, which is what a small graph
+// (Cora-ML: 74 chunks) pays for.  Stored-value form in every step (the value stream of a graph this
+// small is irrelevant), coherent gathers because the source of step k+1 was written in step k.
+template <int VEC, int G, int U, bool FULL_TILE>
+__global__ void __launch_bounds__(256, PPNP_SPMM_MINBLOCKS_WIDE)
+appnp_persistent_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
+                        const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
+                        int64_t n_chunks, int chunk_edges,
+                        const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_row,
+                        const float* __restrict__ fix_deg, int64_t n_fix,
+                        const float* H, float* Z, float* S, float* partial, int ld, int F, int K, float alpha) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const float* src = H;
+    for (int k = 1; k <= K; ++k) {
+        float* dst = ((K - k) % 2 == 0) ? Z : S;
+        spmm_stream_body<VEC, G, true, U, FULL_TILE, true>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, src, H,
+                                                            dst, partial, ld, F, alpha, PPNP_EPI_PLAIN, nullptr);
+        if (n_fix > 0) {
+            grid.sync();
+            fixup_body<VEC, G, true>(fix_ptr, fix_row, fix_deg, n_fix, partial, H, dst, ld, F, alpha, PPNP_EPI_PLAIN);
+        }
+        grid.sync();
+        src = dst;
     }
 }
 
@@ -383,6 +443,70 @@ int dispatch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float*
 #undef PPNP_GO
 }
 
+template <int VEC, int G>
+int launch_persistent(const ppnp_plan_t* p, const float* H, float* Z, float* S, float* partial, int64_t ld, int F,
+                      int K, float alpha, cudaStream_t stream) {
+    constexpr int THREADS = 256;
+    constexpr int U = (VEC == 4) ? ((G >= PPNP_SPMM_U4) ? PPNP_SPMM_U4 : G) : ((G >= 8) ? 8 : G);
+    constexpr int GPW = 32 / G;
+    const int tiles = (F + G * VEC - 1) / (G * VEC);
+    const int64_t groups_per_block = (THREADS / 32) * GPW;
+    const int64_t need = (p->n_chunks + groups_per_block - 1) / groups_per_block;
+    const bool full_tile = (tiles * G * VEC == F);
+    const int smem_bytes = StageCfg<G>::words_per_thread(true) * THREADS * 4;
+    void* kern = full_tile ? (void*)appnp_persistent_kernel<VEC, G, U, true> : (void*)appnp_persistent_kernel<VEC, G, U, false>;
+    int occ = 0;
+    if (smem_bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem_bytes) != cudaSuccess || occ < 1) occ = 1;
+    int64_t cap = (int64_t)sm_count() * occ / tiles;     // every block of the grid must be co-resident
+    if (cap < 1) { set_error("persistent launch: feature tiles exceed the co-resident capacity"); return PPNP_ENOTSUP; }
+    const int64_t gx = need < cap ? need : cap;
+    int chunk_edges = p->chunk_edges, ldi = (int)ld;
+    int64_t n_chunks = p->n_chunks, n_fix = p->n_fix;
+    void* args[] = {(void*)&p->cols, (void*)&p->vals, (void*)&p->seg_row, (void*)&p->chunk_seg, &n_chunks, &chunk_edges,
+                    (void*)&p->fix_ptr, (void*)&p->fix_row, (void*)&p->fix_deg, &n_fix,
+                    (void*)&H, (void*)&Z, (void*)&S, (void*)&partial, &ldi, &F, &K, &alpha};
+    int rc = check_cuda(cudaLaunchCooperativeKernel(kern, dim3((unsigned)gx, (unsigned)tiles), dim3(THREADS), args, smem_bytes, stream),
+                        "cooperative launch appnp_persistent_kernel");
+    return rc;
+}
+
+int dispatch_persistent(const ppnp_plan_t* p, const float* H, float* Z, float* S, float* partial, int64_t ld, int F,
+                        int K, float alpha, cudaStream_t stream) {
+    const bool vec4 = (F % 4 == 0) && (ld % 4 == 0) && aligned16(H) && aligned16(Z) && aligned16(S) &&
+                      (partial == nullptr || aligned16(partial));
+#define PPNP_GO(V_, G_) return launch_persistent<V_, G_>(p, H, Z, S, partial, ld, F, K, alpha, stream)
+    if (vec4) {
+        const int gl = pow2ceil(F / 4);
+        switch (gl >= 32 ? 32 : gl) {
+            case 1: PPNP_GO(4, 1);
+            case 2: PPNP_GO(4, 2);
+            case 4: PPNP_GO(4, 4);
+            case 8: PPNP_GO(4, 8);
+            case 16: PPNP_GO(4, 16);
+            default: PPNP_GO(4, 32);
+        }
+    } else {
+        const int gl = pow2ceil(F);
+        switch (gl >= 32 ? 32 : gl) {
+            case 1: PPNP_GO(1, 1);
+            case 2: PPNP_GO(1, 2);
+            case 4: PPNP_GO(1, 4);
+            case 8: PPNP_GO(1, 8);
+            case 16: PPNP_GO(1, 16);
+            default: PPNP_GO(1, 32);
+        }
+    }
+#undef PPNP_GO
+}
+
+// PPNP_PERSISTENT=0 in the environment forces the per-step launches (A/B measurements)
+bool persistent_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("PPNP_PERSISTENT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 int validate_plan(const ppnp_plan_t* p) {
     PPNP_REQUIRE(p != nullptr, "plan is null");
     PPNP_REQUIRE(p->n > 0 && p->n_chunks > 0 && p->n_edges > 0, "empty plan");
@@ -430,6 +554,11 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
     PPNP_REQUIRE(!(use_vals || (mode == PPNP_MODE_SYM)) || plan->vals != nullptr,
                  "plan->vals required (stored-value steps / first 'sym' step)");
     cudaStream_t stream = as_stream(stream_);
+    // small graphs: all K steps in one cooperative launch (grid barriers instead of 2K launches)
+    if (K >= 2 && plan->vals != nullptr && plan->row_deg == nullptr && plan->n_chunks <= PPNP_PERSISTENT_MAX_CHUNKS &&
+        persistent_enabled()) {
+        return dispatch_persistent(plan, H, Z, scratch, partial, ld, F, K, alpha, stream);
+    }
     const float* src = H;
     for (int k = 1; k <= K; ++k) {
         float* dst = ((K - k) % 2 == 0) ? Z : scratch;
@@ -446,6 +575,21 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
         src = dst;
     }
     return PPNP_OK;
+}
+
+int ppnp_appnp_propagate_persistent(const ppnp_plan_t* plan, const float* H, float* Z, float* scratch, float* partial,
+                                    int64_t ld, int32_t F, int32_t K, float alpha, void* stream_) {
+    using namespace ppnp;
+    int rc = validate_plan(plan);
+    if (rc) return rc;
+    PPNP_REQUIRE(H && Z && scratch, "null matrix pointer");
+    PPNP_REQUIRE(H != Z && H != scratch && Z != scratch, "H, Z, scratch must be distinct buffers");
+    PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
+    PPNP_REQUIRE(K >= 1, "K >= 1");
+    PPNP_REQUIRE(plan->vals != nullptr, "the persistent kernel uses the stored values");
+    PPNP_REQUIRE(plan->row_deg == nullptr, "partial-row streams are not supported here");
+    PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
+    return dispatch_persistent(plan, H, Z, scratch, partial, ld, F, K, alpha, as_stream(stream_));
 }
 
 }  // extern "C"

@@ -55,6 +55,7 @@ struct Vec<1> {
     __device__ __forceinline__ void fma(float w, const Vec& o) { x = fmaf(w, o.x, x); }
     __device__ __forceinline__ static Vec load(const float* p) { Vec v; v.x = __ldg(p); return v; }
     __device__ __forceinline__ static Vec load_plain(const float* p) { Vec v; v.x = *p; return v; }
+    __device__ __forceinline__ static Vec load_cg(const float* p) { Vec v; v.x = __ldcg(p); return v; }
     __device__ __forceinline__ static Vec load_stream(const float* p) { Vec v; v.x = __ldcs(p); return v; }
     __device__ __forceinline__ void store(float* p) const { *p = x; }
     __device__ __forceinline__ void store_stream(float* p) const { __stcs(p, x); }
@@ -72,6 +73,7 @@ struct Vec<4> {
     }
     __device__ __forceinline__ static Vec load(const float* p) { Vec r; r.v = __ldg(reinterpret_cast<const float4*>(p)); return r; }
     __device__ __forceinline__ static Vec load_plain(const float* p) { Vec r; r.v = *reinterpret_cast<const float4*>(p); return r; }
+    __device__ __forceinline__ static Vec load_cg(const float* p) { Vec r; r.v = __ldcg(reinterpret_cast<const float4*>(p)); return r; }
     __device__ __forceinline__ static Vec load_stream(const float* p) { Vec r; r.v = __ldcs(reinterpret_cast<const float4*>(p)); return r; }
     __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
     __device__ __forceinline__ void store_stream(float* p) const { __stcs(reinterpret_cast<float4*>(p), v); }

@@ -260,7 +260,7 @@ class PartitionedPropagation:
         dev = topo.indices.device
         self.on_gpu = dev.type == "cuda"
         if transport == "auto":
-            transport = "pull" if self.on_gpu else "p2p"
+            transport = "pull" if (self.on_gpu and topo.world > 1) else "p2p"
         self.transport_name = transport
         self.transport = PeerPull(topo, group) if transport == "pull" else RoundSendRecv(topo, group)
         P, rank, n_local = topo.world, topo.rank, topo.n_local

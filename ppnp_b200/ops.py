@@ -148,6 +148,21 @@ def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False,
     return Z
 
 
+def appnp_propagate_persistent(graph: PropagationGraph, H, K=10, alpha=0.1):
+    """The K steps in one cooperative launch (csrc/appnp_spmm.cu appnp_persistent_kernel)."""
+    lib = _lib.load()
+    _require_cuda(H)
+    H = H.contiguous()
+    n, F = H.shape
+    Z, scratch = torch.empty_like(H), torch.empty_like(H)
+    partial = graph.partial_buffer(F)
+    with torch.cuda.device(H.device):
+        rc = lib.ppnp_appnp_propagate_persistent(graph.plan.struct(), _lib.ptr(H), _lib.ptr(Z), _lib.ptr(scratch),
+                                                 _lib.ptr(partial), F, F, int(K), float(alpha), _lib.current_stream())
+    _lib.check(rc, "ppnp_appnp_propagate_persistent")
+    return Z
+
+
 class _APPNPFunction(torch.autograd.Function):
     """dH = P_K(A_hat) dZ: the same K-step kernel on the upstream gradient (A_hat symmetric,
     SURVEY.md section 3.3) -- no activations are saved."""

@@ -308,3 +308,40 @@ def test_batch_step_matches_reference_lines(name):
         out.backward(torch.from_numpy(Gn).to(dev()))
         dref = dense[idx_b][:, sel_ref].astype(np.float64).T @ Gn
         assert relerr(Hsub.grad.cpu().numpy(), dref) < 1e-5
+
+
+# ------------------------------------------------------------------ persistent K-step kernel
+@pytest.mark.parametrize("name", NAMES)
+@pytest.mark.parametrize("F", [3, 7, 16, 64])
+def test_persistent_kernel_matches_restatement(name, F):
+    """All K steps in one cooperative launch (grid barriers) == the per-step launches == the oracle."""
+    import ppnp_b200 as P
+    ahat, adj = gpu_ahat(name)
+    A = oracle.calc_A_hat(adj, "sym")
+    Hn = np.random.RandomState(F).randn(adj.shape[0], F).astype(np.float32)
+    H = torch.from_numpy(Hn).to(dev())
+    for order in ("natural", "degree"):
+        graph = P.PropagationGraph(ahat, chunk_edges=128, order=order)
+        for K in (1, 2, 10, 11):
+            ref = oracle.appnp(A, Hn.astype(np.float64), 0.1, K)
+            Zp = P.appnp_propagate_persistent(graph, H, K, 0.1)
+            assert relerr(Zp.cpu().numpy(), ref) < 1e-5, (order, K)
+            Zp2 = P.appnp_propagate_persistent(graph, H, K, 0.1)
+            assert torch.equal(Zp, Zp2)                                  # deterministic
+        # the public entry point picks the persistent kernel for a graph this small
+        Za = P.appnp_propagate(graph, H, 10, 0.1)
+        assert torch.equal(Za, P.appnp_propagate_persistent(graph, H, 10, 0.1))
+
+
+def test_persistent_kernel_on_hub_rows():
+    """Rows split over many chunks need the in-kernel fix-up phase between two grid barriers."""
+    import ppnp_b200 as P
+    ip, idx = oracle.rmat_graph(30000, 500000, 15, seed=2)
+    oip, oidx, oval, _ = oracle.c_a_hat(ip, idx, None, "sym")
+    ahat = P.csr_normalize(torch.from_numpy(ip.astype(np.int32)).to(dev()), torch.from_numpy(idx).to(dev()))
+    graph = P.PropagationGraph(ahat, chunk_edges=128, order="degree")
+    assert graph.plan.n_fix > 0 and graph.plan.n_chunks <= 4096 * 2
+    Hn = np.random.RandomState(0).randn(30000, 16).astype(np.float32)
+    ref = oracle.c_appnp_f64(oip, oidx, oval, Hn.astype(np.float64), 10, 0.1)
+    Z = P.appnp_propagate_persistent(graph, torch.from_numpy(Hn).to(dev()), 10, 0.1)
+    assert relerr(Z.cpu().numpy(), ref) < 1e-5
