@@ -102,6 +102,17 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        if key in d:
+            return d[key]["bytes_per_launch"], d[key]["source"]
+    return None, None
+
+
 def algorithmic_bytes_per_pass(n, nnz, F, value_free=True):
     """per SpMM+axpy step 4(n+1) [indptr] + 4 nnz [indices] (+ 4 nnz [values]) +
     12 n F [read Z once, read H, write Z'].  A pass = 2 x K steps; the value-free iteration still
@@ -273,6 +284,7 @@ def run_ours(args):
     bytes_pass = algorithmic_bytes_per_pass(n, nnz, F, value_free=not args.use_vals)
     achieved = bytes_pass / (ms * 1e-3) / 1e9
     launches_per_pass = 2 * KSTEPS * (2 if graph.plan.n_fix > 0 else 1)
+    traffic, traffic_src = measured_traffic(f"{wl}/{args.order}/{'stored-values' if args.use_vals else 'value-free'}")
 
     # ---- e2e: host buffers through the public API, copies inside the timed region
     e2e_steps = max(2, min(steps, 3))
@@ -325,8 +337,8 @@ def run_ours(args):
                    "order": args.order, "chunk_edges": args.chunk_edges, "l2": "inputs larger than L2 (3 x 512 MB)",
                    "graph_build_s": round(t_build, 2)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "spmm_stream_kernel",
-                     "algorithmic_bytes_per_launch": bytes_pass / (2 * KSTEPS),
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": "spmm_stream_kernel", "algorithmic_bytes_per_launch": bytes_pass / (2 * KSTEPS),
                      "launch_ms": ms / (2 * KSTEPS)},
         "cpu_baseline": cpu,
         "e2e": {"value": work / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
