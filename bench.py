@@ -362,7 +362,7 @@ def main():
     ap.add_argument("--use-vals", action="store_true", help="stored-value form in every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--phases", default="peer", choices=["peer", "two", "one"], help="multi-GPU: how a step is split")
-    ap.add_argument("--transport", default="auto", choices=["auto", "pull", "p2p"], help="multi-GPU: halo transport")
+    ap.add_argument("--transport", default="auto", choices=["auto", "pull", "push", "p2p"], help="multi-GPU: halo transport")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -187,6 +187,64 @@ class PeerPull:
         gather_rows(peer, self.want[owner], src[t.n_local + self.offs[owner]: t.n_local + self.offs[owner] + c])
 
 
+class PeerPush:
+    """Halo transport over peer memory, owner-driven: every rank gathers the rows a peer needs from its
+    local Z (fast, local HBM) and writes them CONTIGUOUSLY into that peer's halo slots through the
+    symmetric-memory mapping (csrc/rows.cu with a peer destination): NVLink sees full-line posted
+    writes instead of 64-byte read round trips.  One device-side barrier per step tells every rank
+    that its halo has landed."""
+
+    def __init__(self, topo: ShardTopology, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.topo, self.group = topo, (group if group is not None else dist.group.WORLD)
+        self.hx = HaloExchange(topo, group)                     # trades the send lists once
+        dev = topo.halo_cols.device
+        P = topo.world
+        mine = torch.tensor(topo.recv_counts + [topo.n_local], dtype=torch.int64, device=dev)
+        allc = torch.empty(P * (P + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        allc = allc.view(P, P + 1).cpu()
+        # where my rows land inside peer q's halo region: after the rows of all owners < me
+        self.dst_off = [int(allc[q, P]) + int(allc[q, : topo.rank].sum()) for q in range(P)]
+        self.soffs, o = [], 0
+        for q in range(P):
+            self.soffs.append(o)
+            o += self.hx.send_counts[q]
+        ext = torch.tensor([topo.n_local + topo.n_halo], dtype=torch.int64, device=dev)
+        dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+        self.rows_alloc = int(ext)
+        self.handles = {}
+
+    def alloc(self, F, count=3):
+        dev = self.topo.halo_cols.device
+        bufs = []
+        for _ in range(count):
+            t = self.symm_mem.empty((self.rows_alloc, F), dtype=torch.float32, device=dev)
+            h = self.symm_mem.rendezvous(t, self.group)
+            self.handles[t.data_ptr()] = (h, F)
+            bufs.append(t)
+        return bufs
+
+    def step_barrier(self, buf):
+        pass                                                    # the barrier after the pushes orders everything
+
+    def push_all(self, src):
+        """Write my rows into every peer's halo slots of the same symmetric buffer, then barrier."""
+        from .ops import gather_rows
+        t = self.topo
+        h, F = self.handles[src.data_ptr()]
+        for d in range(1, t.world):
+            q = (t.rank + d) % t.world                          # start with a different peer on every rank
+            ns = self.hx.send_counts[q]
+            if ns == 0:
+                continue
+            peer = h.get_buffer(q, (self.rows_alloc, F), torch.float32)
+            ids = self.hx.send_idx[self.soffs[q]: self.soffs[q] + ns]
+            gather_rows(src[: t.n_local], ids, peer[self.dst_off[q]: self.dst_off[q] + ns])
+        h.barrier()
+
+
 class RoundSendRecv:
     """Halo transport over torch.distributed point-to-point (NCCL on GPUs, gloo in the CPU tests): the
     rows a peer needs are packed (csrc/rows.cu on CUDA) and sent, its rows for me are received straight
@@ -260,9 +318,12 @@ class PartitionedPropagation:
         dev = topo.indices.device
         self.on_gpu = dev.type == "cuda"
         if transport == "auto":
-            transport = "pull" if (self.on_gpu and topo.world > 1) else "p2p"
+            transport = "push" if (self.on_gpu and topo.world > 1) else "p2p"
+        if transport == "push" and phases == "peer":
+            phases = "two"                                   # pushes complete together: local phase, then remote phase
+        self.phases = phases
         self.transport_name = transport
-        self.transport = PeerPull(topo, group) if transport == "pull" else RoundSendRecv(topo, group)
+        self.transport = {"pull": PeerPull, "push": PeerPush}.get(transport, RoundSendRecv)(topo, group)
         P, rank, n_local = topo.world, topo.rank, topo.n_local
         ip = topo.indptr
         deg = ip[1:] - ip[:-1]
@@ -308,7 +369,7 @@ class PartitionedPropagation:
             del m, cnt, ipp
         del row_of, cols, vals, edge_phase
         self.comm_stream = torch.cuda.Stream(device=dev) if self.on_gpu else None
-        self.exchange = self.transport.hx if isinstance(self.transport, RoundSendRecv) else None
+        self.exchange = getattr(self.transport, "hx", None)
 
     def n_ext(self):
         return self.topo.n_local + self.topo.n_halo
@@ -321,7 +382,9 @@ class PartitionedPropagation:
         ph, owner = rnd
         t = self.topo
         if owner is None:                                  # all owners at once
-            if isinstance(self.transport, PeerPull):
+            if isinstance(self.transport, PeerPush):
+                self.transport.push_all(src)
+            elif isinstance(self.transport, PeerPull):
                 for q in range(t.world):
                     if q != t.rank:
                         self.transport.fetch(src, q)
@@ -570,11 +633,11 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     for p in prop.plans:
         if p is not None:
             launches += 2 if p.plan.n_fix > 0 else 1
-    launches += len(prop.rounds) if prop.transport_name == "pull" else 0
+    launches += (world - 1) if prop.transport_name in ("pull", "push") else 0
     work = 2 * K * nnz * F
     return {
         "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,
-        "partition": {"rule": "contiguous row blocks cut at the non-zero prefix sum", "phases": phases,
+        "partition": {"rule": "contiguous row blocks cut at the non-zero prefix sum", "phases": prop.phases,
                       "transport": prop.transport_name,
                       "rows": [int(s[2]) for s in allstats], "nnz": [int(s[0]) for s in allstats],
                       "halo_rows": [int(s[1]) for s in allstats], "interior_rows": [int(s[3]) for s in allstats]},

@@ -46,7 +46,7 @@ def worker(rank, world, port, mode, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["peer/pull", "peer/p2p", "two/pull", "one/p2p"])
+@pytest.mark.parametrize("mode", ["two/push", "one/push", "peer/pull", "peer/p2p", "two/pull", "one/p2p"])
 def test_partitioned_matches_oracle_on_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
