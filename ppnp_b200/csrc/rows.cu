@@ -18,16 +18,22 @@ gather_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int64_t*
     constexpr int U = 8;                      // rows in flight per group
     const int lane = threadIdx.x & 31;
     const int g = lane / G, lg = lane % G;
-    const int64_t group_global = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + g;
-    const int64_t total_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * GPW;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t total_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // A warp owns GPW * U consecutive destination rows; in round u its GPW groups write GPW
+    // CONSECUTIVE rows, i.e. one contiguous GPW * G * VEC * 4-byte run per store instruction (full
+    // 128-byte lines towards a peer over NVLink instead of 64-byte fragments).
     for (int f0 = 0; f0 < F; f0 += G * VEC) {
         const int f = f0 + lg * VEC;
         const bool active = f < F;
-        for (int64_t r0 = group_global * U; r0 < n_rows; r0 += total_groups * U) {
+        for (int64_t r0 = warp_global * (GPW * U); r0 < n_rows; r0 += total_warps * (GPW * U)) {
             int64_t s[U];
             V v[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) s[u] = (r0 + u < n_rows) ? __ldg(idx + r0 + u) : -1;
+            for (int u = 0; u < U; ++u) {
+                const int64_t r = r0 + u * GPW + g;
+                s[u] = (r < n_rows) ? __ldg(idx + r) : -1;
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 v[u].zero();
@@ -35,7 +41,7 @@ gather_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int64_t*
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (active && s[u] >= 0) v[u].store(dst + (r0 + u) * ld_dst + f);
+                if (active && s[u] >= 0) v[u].store(dst + (r0 + u * GPW + g) * ld_dst + f);
         }
     }
 }

@@ -625,7 +625,17 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
             first = False
     ms_compute = timed(compute_only)
 
-    stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum())], dtype=torch.int64, device=dev)
+    # per-rank (not max-reduced) transfer time and egress volume
+    torch.cuda.synchronize(); dist.barrier()
+    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a_.record()
+    for _ in range(4):
+        transfers_only()
+    b_.record(); torch.cuda.synchronize()
+    my_xfer_us = int(a_.elapsed_time(b_) / 4 * 1e3)
+    hx = getattr(prop.transport, "hx", None)
+    sent_rows = sum(hx.send_counts) if hx is not None else 0
+    stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum()), sent_rows, my_xfer_us], dtype=torch.int64, device=dev)
     allstats = [torch.empty_like(stats) for _ in range(world)]
     dist.all_gather(allstats, stats)
     nnz = int(sum(int(s[0]) for s in allstats))
@@ -640,7 +650,8 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         "partition": {"rule": "contiguous row blocks cut at the non-zero prefix sum", "phases": prop.phases,
                       "transport": prop.transport_name,
                       "rows": [int(s[2]) for s in allstats], "nnz": [int(s[0]) for s in allstats],
-                      "halo_rows": [int(s[1]) for s in allstats], "interior_rows": [int(s[3]) for s in allstats]},
+                      "halo_rows": [int(s[1]) for s in allstats], "interior_rows": [int(s[3]) for s in allstats],
+                      "sent_rows": [int(s[4]) for s in allstats], "transfer_us_per_rank": [int(s[5]) for s in allstats]},
         "e2e": {"value": work / (float(ms_e2e) * 1e-3), "unit": "edge*feature/s", "ms_per_step": float(ms_e2e),
                 "h2d_bytes_per_step": 2 * n * F * 4, "d2h_bytes_per_step": 2 * n * F * 4},
         "gpu_launches": launches * 2 * K * steps, "graph_build_s": round(t_build, 1),
