@@ -464,10 +464,25 @@ class _SubGraph:
 
 
 # ------------------------------------------------------------------------------ shard generation (bench)
-def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group=None):
+def stripe_relabel(ids, n, world, stripes):
+    """Block-cyclic relabelling of the vertex ids: the id space is cut into world * stripes equal
+    blocks that are dealt round-robin, so that every contiguous 1/world-th of the NEW id space holds
+    `stripes` blocks spread over the whole old range.  R-MAT puts its hubs at the low ids: without
+    this, the nnz-balanced contiguous cut gives rank 0 only hubs and the last rank only leaves, and
+    the last rank ships 11x the rows rank 0 does (measured, profiles/r01_scaling.md).  A bijection
+    when n is a multiple of world * stripes (else the ids are returned unchanged)."""
+    if world == 1 or stripes <= 1 or n % (world * stripes) != 0:
+        return ids
+    B = n // (world * stripes)
+    blk = torch.div(ids, B, rounding_mode="floor")
+    return (blk % world) * (n // world) + torch.div(blk, world, rounding_mode="floor") * B + ids % B
+
+
+def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group=None, stripes=16):
     """Rows of A + I of the R-MAT graph owned by ``rank`` (global column ids) and the partition.
     Pass 1 estimates the per-row weight from the raw draws to place the boundaries by non-zeros;
-    pass 2 keeps the (de-duplicated) edges whose row falls inside this rank's block."""
+    pass 2 keeps the (de-duplicated) edges whose row falls inside this rank's block.  Vertex ids
+    are the striped relabelling of the generator's ids (``stripe_relabel``)."""
     from . import _lib
     lib = _lib.load()
 
@@ -475,7 +490,10 @@ def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group
         k = torch.empty(2 * (e1 - e0), dtype=torch.int64, device=dev)
         rc = lib.ppnp_rmat_keys(int(seed), int(scale), int(n), int(e0), int(e1), _lib.ptr(k), _lib.current_stream())
         _lib.check(rc, "ppnp_rmat_keys")
-        return k[k >= 0]
+        k = k[k >= 0]
+        if world > 1 and stripes > 1 and n % (world * stripes) == 0:
+            k = (stripe_relabel(k >> 32, n, world, stripes) << 32) | stripe_relabel(k & 0xFFFFFFFF, n, world, stripes)
+        return k
 
     # pass 1: this rank histograms its slice of the draws, all-reduce -> approximate degrees
     w = torch.ones(n, dtype=torch.int32, device=dev)       # the self loop
@@ -534,12 +552,12 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
     return 1.0 / torch.sqrt(out)
 
 
-def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto"):
+def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=16):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
     t0 = time.perf_counter()
-    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world)
+    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world, stripes=stripes)
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
@@ -647,7 +665,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     work = 2 * K * nnz * F
     return {
         "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,
-        "partition": {"rule": "contiguous row blocks cut at the non-zero prefix sum", "phases": prop.phases,
+        "partition": {"rule": f"block-cyclic relabelling ({stripes} stripes per rank), then contiguous row blocks cut at the non-zero prefix sum", "phases": prop.phases,
                       "transport": prop.transport_name,
                       "rows": [int(s[2]) for s in allstats], "nnz": [int(s[0]) for s in allstats],
                       "halo_rows": [int(s[1]) for s in allstats], "interior_rows": [int(s[3]) for s in allstats],

@@ -21,23 +21,27 @@ def worker(rank, world, port, mode, outdir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from ppnp_b200 import dist as pd
-        n, raw, scale, F, K, alpha = 200_000, 3_000_000, 18, 16, 10, 0.1
+        n, raw, scale, F, K, alpha = 204_800, 3_000_000, 18, 16, 10, 0.1   # multiple of world * 16 stripes
         indptr, cols, bounds = pd.rmat_shard(n, raw, scale, 0, dev, rank, world, batch=1 << 20)
         dinv = pd.global_dinv(indptr, bounds, rank, world, dev)
         topo = pd.build_shard_topology(indptr, cols, bounds, rank)
         phases, transport = mode.split("/")
         prop = pd.PartitionedPropagation(topo, dinv, phases=phases, transport=transport)
         lo, hi = bounds[rank], bounds[rank + 1]
+        # rows are the striped relabelling of the generator's ids: new id -> old id
+        new_of_old = pd.stripe_relabel(torch.arange(n), n, world, 16).numpy()
+        old_of_new = np.argsort(new_of_old)
+        mine = old_of_new[lo:hi]
         Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
         H, Z, S = prop.transport.alloc(F, 3)
         H.zero_()
-        H[: topo.n_local] = torch.from_numpy(Hg[lo:hi]).to(dev)
+        H[: topo.n_local] = torch.from_numpy(Hg[mine]).to(dev)
         out = prop.propagate(H, Z, S, K, alpha).cpu().numpy()
         # oracle on the host: the same recipe through the C generator
         ip, idx = oracle.rmat_graph(n, raw, scale, seed=0)
         oip, oidx, oval, _ = oracle.c_a_hat(ip, idx, None, "sym")
-        assert int(indptr[-1]) == int(oip[hi] - oip[lo])                 # the shard holds exactly its rows of A + I
-        ref = oracle.c_appnp_f64(oip, oidx, oval, Hg.astype(np.float64), K, alpha)[lo:hi]
+        assert int(indptr[-1]) == int((oip[mine + 1] - oip[mine]).sum())  # the shard holds exactly its rows of A + I
+        ref = oracle.c_appnp_f64(oip, oidx, oval, Hg.astype(np.float64), K, alpha)[mine]
         err = relerr(out, ref)
         assert err < 1e-5, err
         with open(os.path.join(outdir, f"ok_{rank}"), "w") as f:
