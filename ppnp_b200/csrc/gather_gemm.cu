@@ -98,6 +98,87 @@ gather_gemm_f32_kernel(const float* __restrict__ Pi, int64_t ld_pi, const int64_
     }
 }
 
+// Wide-C variant (16 < C <= 64): lanes across the output columns, GW_R rows of Pi per warp in
+// registers-as-accumulators.  The Pi tile of the warp and the H tile of the CTA live in shared memory;
+// per 4 k-values a lane issues GW_R broadcast LDS.128 (Pi) + 4*CL LDS.32 (H) for 4*GW_R*CL FMAs, so the
+// FP32 pipe, not shared memory, is the limit (the narrow kernel above needs one LDS per FMA).
+constexpr int GW_R = 8;    // rows per warp
+constexpr int GW_KT = 64;  // k-values per tile
+
+template <int CL>          // columns per lane: 1 (C <= 32) or 2 (C <= 64)
+__global__ void __launch_bounds__(GG_THREADS)
+gather_gemm_f32_wide_kernel(const float* __restrict__ Pi, int64_t ld_pi, const int64_t* __restrict__ idx,
+                            int64_t m, int64_t n, const float* __restrict__ H, int64_t ld_h, int C, int c_base,
+                            float* __restrict__ out, int64_t ld_out, int64_t k_per_split, int use_atomic) {
+    constexpr int CW = 32 * CL;
+    __shared__ __align__(16) float Hs[GW_KT][CW];
+    __shared__ __align__(16) float Ps[GG_THREADS / 32][GW_R][GW_KT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = ((int64_t)blockIdx.x * (GG_THREADS / 32) + warp) * GW_R;
+    const int64_t kbeg = (int64_t)blockIdx.y * k_per_split;
+    const int64_t kend = (kbeg + k_per_split < n) ? kbeg + k_per_split : n;
+    const float* prow[GW_R];
+#pragma unroll
+    for (int r = 0; r < GW_R; ++r) {
+        const int64_t rr = row0 + r;
+        prow[r] = (rr < m) ? Pi + (idx ? idx[rr] : rr) * ld_pi : nullptr;
+    }
+    float acc[GW_R][CL];
+#pragma unroll
+    for (int r = 0; r < GW_R; ++r)
+#pragma unroll
+        for (int j = 0; j < CL; ++j) acc[r][j] = 0.f;
+
+    for (int64_t k0 = kbeg; k0 < kend; k0 += GW_KT) {
+        for (int t = threadIdx.x; t < GW_KT * CW; t += GG_THREADS) {
+            const int kk = t / CW, c = t % CW;
+            const int64_t k = k0 + kk;
+            Hs[kk][c] = (k < kend && c_base + c < C) ? __ldg(H + k * ld_h + c_base + c) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < GW_R; ++r)
+#pragma unroll
+            for (int i = 0; i < GW_KT / 32; ++i) {
+                const int64_t k = k0 + lane + 32 * i;
+                Ps[warp][r][lane + 32 * i] = (prow[r] != nullptr && k < kend) ? __ldcs(prow[r] + k) : 0.f;
+            }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < GW_KT; kk += 4) {
+            float h[4][CL];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < CL; ++j) h[q][j] = Hs[kk + q][lane + 32 * j];
+#pragma unroll
+            for (int r = 0; r < GW_R; ++r) {
+                const float4 p = *reinterpret_cast<const float4*>(&Ps[warp][r][kk]);
+#pragma unroll
+                for (int j = 0; j < CL; ++j) {
+                    acc[r][j] = fmaf(p.x, h[0][j], acc[r][j]);
+                    acc[r][j] = fmaf(p.y, h[1][j], acc[r][j]);
+                    acc[r][j] = fmaf(p.z, h[2][j], acc[r][j]);
+                    acc[r][j] = fmaf(p.w, h[3][j], acc[r][j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < GW_R; ++r) {
+        const int64_t rr = row0 + r;
+        if (rr >= m) continue;
+#pragma unroll
+        for (int j = 0; j < CL; ++j) {
+            const int c = c_base + lane + 32 * j;
+            if (c < C) {
+                float* o = out + rr * ld_out + c;
+                if (use_atomic) atomicAdd(o, acc[r][j]); else *o = acc[r][j];
+            }
+        }
+    }
+}
+
 // adjoint: out[k, c] = sum_r Pi[idx[r], k] * G[r, c]   (dH of model.py:63 as autograd computes it)
 constexpr int GT_RT = 32;
 template <int CP>
@@ -179,6 +260,28 @@ int launch_fwd(const float* Pi, int64_t ld_pi, const int64_t* idx, int64_t m, in
     return PPNP_OK;
 }
 
+template <int CL>
+int launch_fwd_wide(const float* Pi, int64_t ld_pi, const int64_t* idx, int64_t m, int64_t n, const float* H,
+                    int64_t ld_h, int C, int c_base, float* out, int64_t ld_out, cudaStream_t stream) {
+    const int64_t rows_per_cta = (GG_THREADS / 32) * GW_R;
+    const int64_t gx = (m + rows_per_cta - 1) / rows_per_cta;
+    const int64_t ktiles = (n + GW_KT - 1) / GW_KT;
+    int64_t want = (2 * (int64_t)sm_count() + gx - 1) / gx;
+    if (want < 1) want = 1;
+    if (want > ktiles) want = ktiles;
+    const int64_t k_per_split = ((ktiles + want - 1) / want) * GW_KT;
+    const int64_t gy = (n + k_per_split - 1) / k_per_split;
+    const int use_atomic = gy > 1;
+    if (use_atomic && c_base == 0) {
+        int rc = check_cuda(cudaMemset2DAsync(out, ld_out * sizeof(float), 0, (size_t)C * sizeof(float), (size_t)m, stream), "memset out");
+        if (rc) return rc;
+    }
+    gather_gemm_f32_wide_kernel<CL><<<dim3((unsigned)gx, (unsigned)gy), GG_THREADS, 0, stream>>>(
+        Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, k_per_split, use_atomic);
+    PPNP_CHECK_LAUNCH("gather_gemm_f32_wide_kernel");
+    return PPNP_OK;
+}
+
 template <int CP>
 int launch_t(const float* Pi, int64_t ld_pi, const int64_t* idx, int64_t m, int64_t n, const float* G,
              int64_t ld_g, int C, int c_base, float* out, int64_t ld_out, cudaStream_t stream) {
@@ -220,8 +323,8 @@ int ppnp_gather_gemm_f32(const float* Pi, int64_t ld_pi, const int64_t* idx, int
             if (cw <= 4) rc = launch_fwd<4, 4>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
             else if (cw <= 8) rc = launch_fwd<8, 4>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
             else if (cw <= 16) rc = launch_fwd<16, 4>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
-            else if (cw <= 32) rc = launch_fwd<32, 2>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
-            else rc = launch_fwd<64, 1>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
+            else if (cw <= 32) rc = launch_fwd_wide<1>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
+            else rc = launch_fwd_wide<2>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
         } else {
             if (cw <= 4) rc = launch_t<4>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
             else if (cw <= 8) rc = launch_t<8>(Pi, ld_pi, idx, m, n, H, ld_h, C, c_base, out, ld_out, stream);
