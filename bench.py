@@ -222,7 +222,8 @@ def run_ours(args):
     if partitioned:
         from ppnp_b200 import dist as pd
         result = pd.bench_partitioned(wl, n, raw, scale, F, KSTEPS, ALPHA, steps, warmup, dev, rank, world,
-                                       phases=args.phases, transport=args.transport, stripes=args.stripes)
+                                       phases=args.phases, transport=args.transport, stripes=args.stripes,
+                                       row_groups=args.row_groups)
         if rank == 0:
             sampler_clocks = result.pop("clocks")
             nnz = result.pop("nnz")
@@ -361,9 +362,10 @@ def main():
     ap.add_argument("--chunk-edges", type=int, default=256)
     ap.add_argument("--use-vals", action="store_true", help="stored-value form in every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--phases", default="two", choices=["peer", "two", "one"], help="multi-GPU: how a step is split")
-    ap.add_argument("--stripes", type=int, default=16, help="multi-GPU: block-cyclic stripes per rank (1 = plain contiguous blocks)")
-    ap.add_argument("--transport", default="auto", choices=["auto", "pull", "push", "p2p"], help="multi-GPU: halo transport")
+    ap.add_argument("--phases", default="one", choices=["peer", "two", "one"], help="multi-GPU: how a step is split")
+    ap.add_argument("--row-groups", type=int, default=4, help="multi-GPU: kernels per step of the pipelined push")
+    ap.add_argument("--stripes", type=int, default=0, help="multi-GPU: block-cyclic stripes per rank (0 = auto, ~4096-id stripes; 1 = plain contiguous blocks)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "pipe", "pull", "push", "p2p"], help="multi-GPU: halo transport")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

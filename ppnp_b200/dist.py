@@ -322,8 +322,19 @@ class PartitionedPropagation:
         if transport == "push" and phases == "peer":
             phases = "two"                                   # pushes complete together: local phase, then remote phase
         self.phases = phases
+        auto = transport == "push" and self.on_gpu
+        try:
+            self.transport = {"pull": PeerPull, "push": PeerPush}.get(transport, RoundSendRecv)(topo, group)
+            if auto:
+                self.transport.alloc(4, 1)                   # probe: symmetric memory must be usable on this box
+        except Exception as e:  # noqa: BLE001  (peer mapping unavailable: NCCL point-to-point still works)
+            if not auto:
+                raise
+            import warnings
+            warnings.warn(f"ppnp_b200.dist: peer-memory transport unavailable ({type(e).__name__}: {e}); using NCCL p2p")
+            transport = "p2p"
+            self.transport = RoundSendRecv(topo, group)
         self.transport_name = transport
-        self.transport = {"pull": PeerPull, "push": PeerPush}.get(transport, RoundSendRecv)(topo, group)
         P, rank, n_local = topo.world, topo.rank, topo.n_local
         ip = topo.indptr
         deg = ip[1:] - ip[:-1]
@@ -441,6 +452,199 @@ class PartitionedPropagation:
         return Z_ext[: t.n_local]
 
 
+class PipelinedPushPropagation:
+    """K-step APPNP over one shard with a SENDER-side pipelined halo push.
+
+    The shard's rows are cut into ``row_groups`` contiguous groups of equal non-zeros; a step runs one
+    kernel per group.  As soon as group g of step k is final, its rows that peers need are gathered
+    and written into the peers' halo slots of the step-(k+1) source buffer (symmetric memory over
+    NVLink, csrc/rows.cu) on a side stream -- while the kernels of groups g+1.. are still running.
+    Only the push of the LAST group (1/row_groups of the halo) plus one device-side barrier is exposed
+    per step.  Rows are never split between kernels, so there is no accumulate pass and no extra
+    traffic; the arithmetic (and its order) is that of the single-GPU kernel.
+    On CPU tensors (gloo tests) the push is emulated with point-to-point messages of the same slices."""
+
+    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, row_groups=4, group=None, step_fn=None):
+        from .plan import build_stream_plan
+        self.topo, self.group = topo, group
+        dev = topo.indices.device
+        self.on_gpu = dev.type == "cuda"
+        P, rank, n_local = topo.world, topo.rank, topo.n_local
+        ip = topo.indptr
+        deg = ip[1:] - ip[:-1]
+        lo = topo.bounds[rank]
+        dinv_ext = torch.cat([deg_global_dinv[lo: lo + n_local], deg_global_dinv[topo.halo_cols]])
+        row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), deg)
+        vals = dinv_ext[row_of] * dinv_ext[topo.indices.to(torch.int64)]
+        del row_of
+        G = max(1, min(row_groups, n_local))
+        self.gb = balanced_row_blocks(deg, G)                     # local row boundaries of the groups
+        self.plans = []
+        for g in range(G):
+            a, b = self.gb[g], self.gb[g + 1]
+            if b <= a:
+                self.plans.append(None)
+                continue
+            rows = torch.arange(a, b, device=dev)
+            order = rows[torch.sort(deg[a:b], descending=True, stable=True).indices]
+            self.plans.append(_SubGraph(build_stream_plan(ip, topo.indices, vals, chunk_edges, order, subset=True), step_fn))
+        del vals
+        self.G = G
+        # send lists (sorted local ids per destination) cut at the group boundaries
+        self.hx = HaloExchange(topo, group)
+        gbt = torch.tensor(self.gb, dtype=torch.int64, device=dev)
+        self.soffs, o = [], 0
+        scnt = torch.zeros((P, G), dtype=torch.int64)
+        for q in range(P):
+            self.soffs.append(o)
+            ns = self.hx.send_counts[q]
+            if ns:
+                ids = self.hx.send_idx[o: o + ns]
+                cuts = torch.searchsorted(ids, gbt)                # position of every group boundary in the list
+                scnt[q] = (cuts[1:] - cuts[:-1]).cpu()
+            o += ns
+        self.scnt = scnt                                          # rows I send to q out of my group g
+        # what every peer sends me per group, and where my rows land at every peer
+        allc = torch.empty(P * P * G, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, scnt.to(dev).flatten().contiguous(), group=group)
+        allc = allc.view(P, P, G).cpu()                           # allc[s, q, g]: s sends q in s's group g
+        self.rcnt = allc[:, rank, :].clone()                      # [source, g]
+        mine = torch.tensor(topo.recv_counts + [topo.n_local], dtype=torch.int64, device=dev)
+        rc_all = torch.empty(P * (P + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(rc_all, mine, group=group)
+        rc_all = rc_all.view(P, P + 1).cpu()
+        # my rows for q land after q's local rows and after the rows of all owners < me
+        self.dst_off = [int(rc_all[q, P]) + int(rc_all[q, :rank].sum()) for q in range(P)]
+        self.roffs, o = [], 0
+        for q in range(P):
+            self.roffs.append(o)
+            o += topo.recv_counts[q]
+        for q in range(P):                                        # consistency of the two views of the halo
+            assert int(self.rcnt[q].sum()) == topo.recv_counts[q]
+        ext = torch.tensor([topo.n_local + topo.n_halo], dtype=torch.int64, device=dev)
+        dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+        self.rows_alloc = int(ext)
+        self.handles = {}
+        self._sendbuf = {}
+        self.comm_stream = torch.cuda.Stream(device=dev) if self.on_gpu else None
+        self.transport_name = "pipelined-push" if self.on_gpu else "pipelined-p2p"
+        self.phases = f"{G} row groups"
+        self.rounds = []
+
+    # -- buffers
+    def alloc(self, F, count=3):
+        dev = self.topo.indices.device
+        if not self.on_gpu:
+            return [torch.zeros((self.rows_alloc, F), dtype=torch.float32, device=dev) for _ in range(count)]
+        import torch.distributed._symmetric_memory as symm_mem
+        bufs = []
+        for _ in range(count):
+            t = symm_mem.empty((self.rows_alloc, F), dtype=torch.float32, device=dev)
+            h = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            self.handles[t.data_ptr()] = (h, F)
+            bufs.append(t)
+        return bufs
+
+    def n_ext(self):
+        return self.topo.n_local + self.topo.n_halo
+
+    # -- transfers
+    def _push_group(self, buf, g):
+        """Ship the rows of my group g that peers need into their halo slots of ``buf``."""
+        t = self.topo
+        P, rank = t.world, t.rank
+        if self.on_gpu:
+            from .ops import gather_rows
+            h, F = self.handles[buf.data_ptr()]
+            for d in range(1, P):
+                q = (rank + d) % P
+                ns = int(self.scnt[q, g])
+                if ns == 0:
+                    continue
+                s0 = self.soffs[q] + int(self.scnt[q, :g].sum())
+                peer = h.get_buffer(q, (self.rows_alloc, F), torch.float32)
+                o = self.dst_off[q] + int(self.scnt[q, :g].sum())
+                gather_rows(buf[: t.n_local], self.hx.send_idx[s0: s0 + ns], peer[o: o + ns])
+        else:
+            ops, keep = [], []
+            for d in range(1, P):
+                q, s = (rank + d) % P, (rank - d) % P
+                ns = int(self.scnt[q, g])
+                if ns:
+                    s0 = self.soffs[q] + int(self.scnt[q, :g].sum())
+                    sb = torch.index_select(buf[: t.n_local], 0, self.hx.send_idx[s0: s0 + ns])
+                    keep.append(sb)
+                    ops.append(dist.P2POp(dist.isend, sb, q, self.group))
+                nr = int(self.rcnt[s, g])
+                if nr:
+                    o = t.n_local + self.roffs[s] + int(self.rcnt[s, :g].sum())
+                    ops.append(dist.P2POp(dist.irecv, buf[o: o + nr], s, self.group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+
+    def _barrier(self, buf):
+        if self.on_gpu:
+            self.handles[buf.data_ptr()][0].barrier()
+
+    def transfers_only(self, buf):
+        for g in range(self.G):
+            self._push_group(buf, g)
+        self._barrier(buf)
+
+    # -- the iteration
+    def propagate(self, H_ext, Z_ext, S_ext, K, alpha):
+        from . import _lib
+        t = self.topo
+        multi = t.world > 1
+        cur = torch.cuda.current_stream() if self.on_gpu else None
+        ready = None
+        if multi:                                              # halo of the input for step 1
+            if self.on_gpu:
+                self.comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self.comm_stream):
+                    self.transfers_only(H_ext)
+                    ready = torch.cuda.Event()
+                    ready.record(self.comm_stream)
+            else:
+                self.transfers_only(H_ext)
+        src = H_ext
+        for k in range(1, K + 1):
+            dst = Z_ext if (K - k) % 2 == 0 else S_ext
+            if K == 1:
+                epi, use_vals = _lib.EPI_PLAIN, True
+            elif k == 1:
+                epi, use_vals = _lib.EPI_Z2Y, True
+            elif k == K:
+                epi, use_vals = _lib.EPI_Y2Z, False
+            else:
+                epi, use_vals = _lib.EPI_Y, False
+            if ready is not None:
+                cur.wait_event(ready)
+            push = multi and k < K
+            for g in range(self.G):
+                if self.plans[g] is not None:
+                    self.plans[g].step(src, H_ext, dst, alpha, epi, use_vals)
+                if push:
+                    if self.on_gpu:
+                        ev = torch.cuda.Event()
+                        ev.record(cur)
+                        with torch.cuda.stream(self.comm_stream):
+                            self.comm_stream.wait_event(ev)
+                            self._push_group(dst, g)
+                    else:
+                        self._push_group(dst, g)
+            if push and self.on_gpu:
+                with torch.cuda.stream(self.comm_stream):
+                    self._barrier(dst)
+                    ready = torch.cuda.Event()
+                    ready.record(self.comm_stream)
+            else:
+                ready = None
+            src = dst
+        return Z_ext[: t.n_local]
+
+
 class _SubGraph:
     def __init__(self, plan, step_fn=None):
         self.plan, self._step_fn = plan, step_fn
@@ -478,13 +682,27 @@ def stripe_relabel(ids, n, world, stripes):
     return (blk % world) * (n // world) + torch.div(blk, world, rounding_mode="floor") * B + ids % B
 
 
-def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group=None, stripes=16):
+def auto_stripes(n, world, target_block=4096):
+    """Stripes per rank such that a stripe is ~target_block ids and world * stripes divides n (0 if none):
+    fine enough that the few hundred thousand hub ids of an R-MAT graph are dealt evenly to all ranks."""
+    if world == 1 or n % world != 0:
+        return 1
+    per = n // world
+    for b in range(target_block, 255, -1):
+        if per % b == 0:
+            return per // b
+    return 1
+
+
+def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group=None, stripes=0):
     """Rows of A + I of the R-MAT graph owned by ``rank`` (global column ids) and the partition.
     Pass 1 estimates the per-row weight from the raw draws to place the boundaries by non-zeros;
     pass 2 keeps the (de-duplicated) edges whose row falls inside this rank's block.  Vertex ids
     are the striped relabelling of the generator's ids (``stripe_relabel``)."""
     from . import _lib
     lib = _lib.load()
+    if stripes == 0:
+        stripes = auto_stripes(n, world)
 
     def keys_of(e0, e1):
         k = torch.empty(2 * (e1 - e0), dtype=torch.int64, device=dev)
@@ -552,20 +770,25 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
     return 1.0 / torch.sqrt(out)
 
 
-def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=16):
+def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
     t0 = time.perf_counter()
+    if stripes == 0:
+        stripes = auto_stripes(n, world)
     indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world, stripes=stripes)
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
-    prop = PartitionedPropagation(topo, dinv, phases=phases, transport=transport)
+    if transport in ("auto", "pipe") and world > 1:
+        prop = PipelinedPushPropagation(topo, dinv, row_groups=row_groups)
+    else:
+        prop = PartitionedPropagation(topo, dinv, phases=phases, transport=("p2p" if transport == "pipe" else transport))
     del dinv
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
-    H, G, Z, S = prop.transport.alloc(F, 4)
+    H, G, Z, S = (prop.alloc(F, 4) if isinstance(prop, PipelinedPushPropagation) else prop.transport.alloc(F, 4))
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     for b in (H, G, Z, S):
         b.zero_()
@@ -630,6 +853,10 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     from . import _lib as _l
 
     def transfers_only():
+        if isinstance(prop, PipelinedPushPropagation):
+            if world > 1:
+                prop.transfers_only(Z)
+            return
         prop.transport.step_barrier(Z)
         for rnd in (prop.rounds or ([(1, None)] if world > 1 else [])):
             prop._transfer(Z, rnd)
@@ -639,7 +866,8 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         first = True
         for p in prop.plans:
             if p is not None:
-                p.step(Z, H if first else S, S, alpha, _l.EPI_Y | (0 if first else _l.EPI_ACC), False)
+                acc_pass = (not first) and not isinstance(prop, PipelinedPushPropagation)
+                p.step(Z, S if acc_pass else H, S, alpha, _l.EPI_Y | (_l.EPI_ACC if acc_pass else 0), False)
             first = False
     ms_compute = timed(compute_only)
 
@@ -651,7 +879,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         transfers_only()
     b_.record(); torch.cuda.synchronize()
     my_xfer_us = int(a_.elapsed_time(b_) / 4 * 1e3)
-    hx = getattr(prop.transport, "hx", None)
+    hx = prop.hx if isinstance(prop, PipelinedPushPropagation) else getattr(prop.transport, "hx", None)
     sent_rows = sum(hx.send_counts) if hx is not None else 0
     stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum()), sent_rows, my_xfer_us], dtype=torch.int64, device=dev)
     allstats = [torch.empty_like(stats) for _ in range(world)]
@@ -662,6 +890,8 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         if p is not None:
             launches += 2 if p.plan.n_fix > 0 else 1
     launches += (world - 1) if prop.transport_name in ("pull", "push") else 0
+    if isinstance(prop, PipelinedPushPropagation):
+        launches += (world - 1) * prop.G
     work = 2 * K * nnz * F
     return {
         "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,
