@@ -365,7 +365,7 @@ def main():
     ap.add_argument("--phases", default="one", choices=["peer", "two", "one"], help="multi-GPU: how a step is split")
     ap.add_argument("--row-groups", type=int, default=4, help="multi-GPU: kernels per step of the pipelined push")
     ap.add_argument("--stripes", type=int, default=0, help="multi-GPU: block-cyclic stripes per rank (0 = auto, ~4096-id stripes; 1 = plain contiguous blocks)")
-    ap.add_argument("--transport", default="auto", choices=["auto", "pipe", "pull", "push", "p2p"], help="multi-GPU: halo transport")
+    ap.add_argument("--transport", default="auto", choices=["auto", "fused", "pipe", "pull", "push", "p2p"], help="multi-GPU: halo transport")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -43,6 +43,9 @@ extern "C" {
  * ppnp_b200/dist.py: local columns first, halo columns once they have arrived). */
 #define PPNP_EPI_ACC 16
 
+/* peers addressable by the fused halo push (ppnp_spmm_step_push): ranks of one NVSwitch domain */
+#define PPNP_MAX_PEERS 8
+
 /* bit 31 of a stream column: last edge of its segment; of a seg_row entry: partial segment */
 #define PPNP_FLAG 0x80000000u
 
@@ -113,6 +116,17 @@ typedef struct ppnp_plan {
 int ppnp_spmm_step(const ppnp_plan_t* plan, const float* Zin, const float* T, float* Zout,
                    float* partial, int64_t ld, int32_t F, float alpha, int32_t epi,
                    int32_t use_vals, void* stream);
+
+/* The same step with the halo push FUSED into the epilogue (partitioned propagation, no counterpart in
+ * the single-process reference): every finished row r with push_ptr[r] < push_ptr[r+1] is also
+ * written to peer_bases[code >> 28] + (code & 0x0fffffff) * ld for code in push_code[push_ptr[r] ..
+ * push_ptr[r+1]) -- the halo slots of that row in the peers' mappings (NVLink peer memory) of the
+ * output buffer.  peer_bases_host is a HOST array of n_peers device pointers.  The caller orders
+ * the next step after these writes with a barrier across the ranks. */
+int ppnp_spmm_step_push(const ppnp_plan_t* plan, const float* Zin, const float* T, float* Zout,
+                        float* partial, int64_t ld, int32_t F, float alpha, int32_t epi,
+                        int32_t use_vals, const int32_t* push_ptr, const int32_t* push_code,
+                        const void* const* peer_bases_host, int32_t n_peers, void* stream);
 
 /* K steps from Z_0 = H.  mode PPNP_MODE_SYM: value-free Y-space iteration when plan->vals is
  * given only for the first step (use_vals == 0), stored values every step when use_vals != 0.

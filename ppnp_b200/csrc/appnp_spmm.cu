@@ -43,6 +43,25 @@ constexpr unsigned FULL = 0xffffffffu;
 
 // Finish a segment: either park the partial sum or apply the epilogue and stream the row out.
 // Kept out of line so that the (rarely taken, per segment end) code exists once in the kernel.
+// Fused halo push (partitioned propagation): a finished row that peers reference is written straight
+// into their halo slots over NVLink from the epilogue -- compute and transfer in ONE kernel, the
+// exchange overlaps the gathers row by row and nothing but a barrier is left between two steps.
+// code = (peer << 28) | row slot in the peer's buffer; base[] = the peers' mappings of the output buffer.
+struct PushArgs {
+    const int32_t* ptr;    // [n + 1] per-row ranges into code[], or nullptr (no pushes)
+    const int32_t* code;
+    float* base[PPNP_MAX_PEERS];
+};
+
+template <int VEC>
+__device__ __forceinline__ void push_row(const Vec<VEC>& o, int row, int ld, int f, const PushArgs* pa) {
+    const int b = __ldg(pa->ptr + row), e = __ldg(pa->ptr + row + 1);
+    for (int i = b; i < e; ++i) {
+        const int code = __ldg(pa->code + i);
+        o.store(pa->base[(code >> 28) & (PPNP_MAX_PEERS - 1)] + (int64_t)(code & 0x0fffffff) * ld + f);
+    }
+}
+
 template <typename V, bool COHERENT>
 __device__ __forceinline__ V gather_load(const float* p) {
     if (COHERENT) return V::load_cg(p);
@@ -52,7 +71,8 @@ __device__ __forceinline__ V gather_load(const float* p) {
 template <int VEC>
 __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t, int sv, float deg, bool active,
                                           float* Zout, float* __restrict__ partial, int ld, int f,
-                                          float alpha, int epi, const float* __restrict__ row_deg) {
+                                          float alpha, int epi, const float* __restrict__ row_deg,
+                                          const PushArgs* pa) {
     if (!active) return;
     if (sv < 0) {
         acc.store(partial + (int64_t)(sv & 0x7fffffff) * ld + f);
@@ -60,7 +80,9 @@ __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t
         float a, bb;
         if (row_deg != nullptr) deg = __ldg(row_deg + sv);   // stream holds only part of the row
         epi_coef(epi, alpha, deg, a, bb);
-        Vec<VEC>::axpby(a, acc, bb, t).store_stream(Zout + (int64_t)sv * ld + f);
+        const Vec<VEC> o = Vec<VEC>::axpby(a, acc, bb, t);
+        o.store_stream(Zout + (int64_t)sv * ld + f);
+        if (pa->ptr != nullptr) push_row<VEC>(o, sv, ld, f, pa);
     }
 }
 
@@ -100,7 +122,7 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
                  int64_t n_chunks, int chunk_edges,
                  const float* Zin, const float* T,
                  float* Zout, float* partial,   // T may alias Zout (PPNP_EPI_ACC)
-                 int ld, int F, float alpha, int epi, const float* __restrict__ row_deg) {
+                 int ld, int F, float alpha, int epi, const float* __restrict__ row_deg, const PushArgs* pa) {
     using V = Vec<VEC>;
     using SC = StageCfg<G>;
     constexpr int GPW = 32 / G;                     // groups per warp
@@ -269,7 +291,7 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
                                 const int pos = j * SE + r * G + u0 + u;
                                 {   // copies: the out-of-line call takes references, acc itself must stay in registers
                                     const V a2 = acc, t2 = t[u];
-                                    emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi, row_deg);
+                                    emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi, row_deg, pa);
                                 }
                                 acc.zero();
                                 seg_begin = pos + 1;
@@ -289,9 +311,10 @@ __global__ void __launch_bounds__(256, (G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOC
 spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
                    const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
                    int64_t n_chunks, int chunk_edges, const float* Zin, const float* T, float* Zout,
-                   float* partial, int ld, int F, float alpha, int epi, const float* __restrict__ row_deg) {
+                   float* partial, int ld, int F, float alpha, int epi, const float* __restrict__ row_deg,
+                   const __grid_constant__ PushArgs pa) {
     spmm_stream_body<VEC, G, HAS_VAL, U, FULL_TILE, false>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, Zin, T,
-                                                           Zout, partial, ld, F, alpha, epi, row_deg);
+                                                           Zout, partial, ld, F, alpha, epi, row_deg, &pa);
 }
 
 // Rows split over several segments: add the partial sums in slot order, then the epilogue.
@@ -299,7 +322,7 @@ template <int VEC, int G, bool COHERENT>
 __device__ __forceinline__ void
 fixup_body(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_row,
            const float* __restrict__ fix_deg, int64_t n_fix, const float* partial,
-           const float* T, float* Zout, int64_t ld, int F, float alpha, int epi) {
+           const float* T, float* Zout, int64_t ld, int F, float alpha, int epi, const PushArgs* pa) {
     using V = Vec<VEC>;
     constexpr int GPW = 32 / G;
     constexpr int U = 8;
@@ -326,7 +349,9 @@ fixup_body(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_
             for (; s < s1; ++s) acc.add(COHERENT ? V::load_cg(partial + (int64_t)s * ld + f) : V::load_plain(partial + (int64_t)s * ld + f));
             float a, bb;
             epi_coef(epi, alpha, __ldg(fix_deg + q), a, bb);
-            V::axpby(a, acc, bb, t).store_stream(Zout + (int64_t)row * ld + f);
+            const V o = V::axpby(a, acc, bb, t);
+            o.store_stream(Zout + (int64_t)row * ld + f);
+            if (pa->ptr != nullptr) push_row<VEC>(o, row, (int)ld, f, pa);
         }
     }
 }
@@ -335,8 +360,9 @@ template <int VEC, int G>
 __global__ void __launch_bounds__(256)
 fixup_kernel(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_row,
              const float* __restrict__ fix_deg, int64_t n_fix, const float* __restrict__ partial,
-             const float* T, float* Zout, int64_t ld, int F, float alpha, int epi) {
-    fixup_body<VEC, G, false>(fix_ptr, fix_row, fix_deg, n_fix, partial, T, Zout, ld, F, alpha, epi);
+             const float* T, float* Zout, int64_t ld, int F, float alpha, int epi,
+             const __grid_constant__ PushArgs pa) {
+    fixup_body<VEC, G, false>(fix_ptr, fix_row, fix_deg, n_fix, partial, T, Zout, ld, F, alpha, epi, &pa);
 }
 
 // All K steps in ONE cooperative launch (north_star: "all K iterations in one persistent launch where
@@ -352,14 +378,17 @@ appnp_persistent_kernel(const int32_t* __restrict__ cols, const float* __restric
                         const float* __restrict__ fix_deg, int64_t n_fix,
                         const float* H, float* Z, float* S, float* partial, int ld, int F, int K, float alpha) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ PushArgs no_push;
+    if (threadIdx.x == 0) no_push.ptr = nullptr;
+    __syncthreads();
     const float* src = H;
     for (int k = 1; k <= K; ++k) {
         float* dst = ((K - k) % 2 == 0) ? Z : S;
         spmm_stream_body<VEC, G, true, U, FULL_TILE, true>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, src, H,
-                                                            dst, partial, ld, F, alpha, PPNP_EPI_PLAIN, nullptr);
+                                                            dst, partial, ld, F, alpha, PPNP_EPI_PLAIN, nullptr, &no_push);
         if (n_fix > 0) {
             grid.sync();
-            fixup_body<VEC, G, true>(fix_ptr, fix_row, fix_deg, n_fix, partial, H, dst, ld, F, alpha, PPNP_EPI_PLAIN);
+            fixup_body<VEC, G, true>(fix_ptr, fix_row, fix_deg, n_fix, partial, H, dst, ld, F, alpha, PPNP_EPI_PLAIN, &no_push);
         }
         grid.sync();
         src = dst;
@@ -380,7 +409,7 @@ int blocks_per_sm(K kernel, int threads, int smem_bytes) {
 
 template <int VEC, int G>
 int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Zout, float* partial,
-                int64_t ld, int F, float alpha, int epi, bool use_vals, cudaStream_t stream) {
+                int64_t ld, int F, float alpha, int epi, bool use_vals, const PushArgs& pa, cudaStream_t stream) {
     constexpr int THREADS = 256;
     constexpr int U = (VEC == 4) ? ((G >= PPNP_SPMM_U4) ? PPNP_SPMM_U4 : G) : ((G >= 8) ? 8 : G);
     constexpr int GPW = 32 / G;
@@ -397,7 +426,7 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
         const int64_t cap = (int64_t)sm_count() * occ;                                                             \
         dim3 grid((unsigned)(need < cap ? need : cap), (unsigned)tiles);                                           \
         k<<<grid, THREADS, smem_bytes, stream>>>(p->cols, HV_ ? p->vals : nullptr, p->seg_row, p->chunk_seg, p->n_chunks, \
-                                        p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi, p->row_deg); \
+                                        p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi, p->row_deg, pa); \
     } while (0)
     if (use_vals) { if (full_tile) PPNP_LAUNCH(true, true); else PPNP_LAUNCH(true, false); }
     else          { if (full_tile) PPNP_LAUNCH(false, true); else PPNP_LAUNCH(false, false); }
@@ -408,17 +437,17 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
         const int64_t capf = (int64_t)sm_count() * 8;
         dim3 grid((unsigned)(needf < capf ? needf : capf), (unsigned)tiles);
         fixup_kernel<VEC, G><<<grid, THREADS, 0, stream>>>(p->fix_ptr, p->fix_row, p->fix_deg, p->n_fix, partial, T,
-                                                           Zout, ld, F, alpha, epi);
+                                                           Zout, ld, F, alpha, epi, pa);
         PPNP_CHECK_LAUNCH("fixup_kernel");
     }
     return PPNP_OK;
 }
 
 int dispatch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Zout, float* partial,
-                  int64_t ld, int F, float alpha, int epi, bool use_vals, cudaStream_t stream) {
+                  int64_t ld, int F, float alpha, int epi, bool use_vals, const PushArgs& pa, cudaStream_t stream) {
     const bool vec4 = (F % 4 == 0) && (ld % 4 == 0) && aligned16(Zin) && aligned16(T) && aligned16(Zout) &&
                       (partial == nullptr || aligned16(partial));
-#define PPNP_GO(V_, G_) return launch_step<V_, G_>(p, Zin, T, Zout, partial, ld, F, alpha, epi, use_vals, stream)
+#define PPNP_GO(V_, G_) return launch_step<V_, G_>(p, Zin, T, Zout, partial, ld, F, alpha, epi, use_vals, pa, stream)
     if (vec4) {
         const int gl = pow2ceil(F / 4);
         switch (gl >= 32 ? 32 : gl) {
@@ -536,7 +565,8 @@ int ppnp_spmm_step(const ppnp_plan_t* plan, const float* Zin, const float* T, fl
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
     PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~31) == 0, "bad epilogue");
     PPNP_REQUIRE(!(epi & PPNP_EPI_ACC) || T == Zout, "PPNP_EPI_ACC adds to the output: pass T == Zout");
-    return dispatch_step(plan, Zin, T, Zout, partial, ld, F, alpha, epi, use_vals != 0, as_stream(stream));
+    PushArgs none{};
+    return dispatch_step(plan, Zin, T, Zout, partial, ld, F, alpha, epi, use_vals != 0, none, as_stream(stream));
 }
 
 int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, float* scratch, float* partial,
@@ -570,11 +600,34 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
         else if (k == 1) { epi = PPNP_EPI_Z2Y; vals = true; }
         else if (k == K) { epi = PPNP_EPI_Y2Z; vals = false; }
         else { epi = PPNP_EPI_Y; vals = false; }
-        rc = dispatch_step(plan, src, H, dst, partial, ld, F, alpha, epi, vals, stream);
+        PushArgs none{};
+        rc = dispatch_step(plan, src, H, dst, partial, ld, F, alpha, epi, vals, none, stream);
         if (rc) return rc;
         src = dst;
     }
     return PPNP_OK;
+}
+
+int ppnp_spmm_step_push(const ppnp_plan_t* plan, const float* Zin, const float* T, float* Zout, float* partial,
+                        int64_t ld, int32_t F, float alpha, int32_t epi, int32_t use_vals, const int32_t* push_ptr,
+                        const int32_t* push_code, const void* const* peer_bases_host, int32_t n_peers, void* stream) {
+    using namespace ppnp;
+    int rc = validate_plan(plan);
+    if (rc) return rc;
+    PPNP_REQUIRE(Zin && T && Zout, "null matrix pointer");
+    PPNP_REQUIRE(Zin != Zout, "Zout must not alias Zin");
+    PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
+    PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
+    PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
+    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~31) == 0, "bad epilogue");
+    PPNP_REQUIRE(push_ptr == nullptr || (push_code && peer_bases_host && n_peers >= 1 && n_peers <= PPNP_MAX_PEERS),
+                 "push lists need codes and 1..PPNP_MAX_PEERS peer base pointers");
+    PushArgs pa{};
+    pa.ptr = push_ptr;
+    pa.code = push_code;
+    for (int i = 0; i < PPNP_MAX_PEERS; ++i)
+        pa.base[i] = (push_ptr && i < n_peers) ? reinterpret_cast<float*>(const_cast<void*>(peer_bases_host[i])) : nullptr;
+    return dispatch_step(plan, Zin, T, Zout, partial, ld, F, alpha, epi, use_vals != 0, pa, as_stream(stream));
 }
 
 int ppnp_appnp_propagate_persistent(const ppnp_plan_t* plan, const float* H, float* Z, float* scratch, float* partial,

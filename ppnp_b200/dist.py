@@ -645,6 +645,202 @@ class PipelinedPushPropagation:
         return Z_ext[: t.n_local]
 
 
+class FusedPushPropagation:
+    """K-step APPNP over one shard with the halo push FUSED into the propagation kernel.
+
+    One kernel per step, the single-GPU one: whenever its epilogue finishes a row that other ranks
+    reference, it also stores the row into those ranks' halo slots of the step's output buffer
+    through the NVLink peer mappings (symmetric memory; csrc/appnp_spmm.cu push_row).  The transfer
+    therefore overlaps the gathers row by row, there is no pack, no collective and no second kernel;
+    a device-side barrier between two steps is all that is left of the exchange.  Only the halo of
+    the INPUT of a propagation (rows of H, produced by the caller) is shipped by a separate gather
+    kernel (csrc/rows.cu) once per call.
+    On CPU tensors (gloo tests) the same push lists are applied with point-to-point messages."""
+
+    MAX_PEERS = 8
+
+    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, group=None, step_fn=None):
+        import ctypes as C
+        from .plan import build_stream_plan
+        self.topo, self.group, self._step_fn = topo, group, step_fn
+        dev = topo.indices.device
+        self.on_gpu = dev.type == "cuda"
+        P, rank, n_local = topo.world, topo.rank, topo.n_local
+        if P > self.MAX_PEERS:
+            raise ValueError(f"the fused push addresses at most {self.MAX_PEERS} ranks")
+        ip = topo.indptr
+        deg = ip[1:] - ip[:-1]
+        lo = topo.bounds[rank]
+        dinv_ext = torch.cat([deg_global_dinv[lo: lo + n_local], deg_global_dinv[topo.halo_cols]])
+        row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), deg)
+        vals = dinv_ext[row_of] * dinv_ext[topo.indices.to(torch.int64)]
+        del row_of
+        order = torch.sort(deg, descending=True, stable=True).indices
+        self.sub = _SubGraph(build_stream_plan(ip, topo.indices, vals, chunk_edges, order), step_fn)
+        self.plans = [self.sub]
+        del vals
+        # push lists: for every local row, the (peer, slot) pairs that want it
+        self.hx = HaloExchange(topo, group)
+        mine = torch.tensor(topo.recv_counts + [topo.n_local], dtype=torch.int64, device=dev)
+        rc_all = torch.empty(P * (P + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(rc_all, mine, group=group)
+        rc_all = rc_all.view(P, P + 1).cpu()
+        self.dst_off = [int(rc_all[q, P]) + int(rc_all[q, :rank].sum()) for q in range(P)]
+        ext = torch.tensor([topo.n_local + topo.n_halo], dtype=torch.int64, device=dev)
+        dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
+        self.rows_alloc = int(ext)
+        if self.rows_alloc >= (1 << 28):
+            raise ValueError("shard too large for the 28-bit slot field of the push code")
+        rows, codes, self.soffs, o = [], [], [], 0
+        for q in range(P):
+            self.soffs.append(o)
+            ns = self.hx.send_counts[q]
+            if ns:
+                rows.append(self.hx.send_idx[o: o + ns])
+                codes.append((q << 28) + self.dst_off[q] + torch.arange(ns, device=dev, dtype=torch.int64))
+            o += ns
+        if rows:
+            rows, codes = torch.cat(rows), torch.cat(codes)
+            perm = torch.sort(rows, stable=True).indices
+            rows, codes = rows[perm], codes[perm]
+            cnt = torch.bincount(rows, minlength=n_local)
+        else:
+            rows = torch.zeros(0, dtype=torch.int64, device=dev)
+            codes, cnt = rows.clone(), torch.zeros(n_local, dtype=torch.int64, device=dev)
+        pp = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
+        pp[1:] = torch.cumsum(cnt, 0)
+        self.push_ptr = pp.to(torch.int32).contiguous()
+        self.push_code = torch.cat([codes, torch.zeros(1, dtype=torch.int64, device=dev)]).to(torch.int32).contiguous()
+        self.push_rows = rows                                     # (CPU emulation)
+        self.handles, self._bases = {}, {}
+        self._C = C
+        self.transport_name = "fused-push" if self.on_gpu else "fused-p2p"
+        self.phases, self.rounds = "one kernel per step, push in the epilogue", []
+
+    def alloc(self, F, count=3):
+        dev = self.topo.indices.device
+        if not self.on_gpu:
+            return [torch.zeros((self.rows_alloc, F), dtype=torch.float32, device=dev) for _ in range(count)]
+        import torch.distributed._symmetric_memory as symm_mem
+        bufs = []
+        grp = self.group if self.group is not None else dist.group.WORLD
+        for _ in range(count):
+            t = symm_mem.empty((self.rows_alloc, F), dtype=torch.float32, device=dev)
+            h = symm_mem.rendezvous(t, grp)
+            self.handles[t.data_ptr()] = (h, F)
+            arr = (self._C.c_void_p * self.MAX_PEERS)()
+            for q in range(self.topo.world):
+                arr[q] = t.data_ptr() if q == self.topo.rank else h.get_buffer(q, (self.rows_alloc, F), torch.float32).data_ptr()
+            self._bases[t.data_ptr()] = arr
+            bufs.append(t)
+        return bufs
+
+    def n_ext(self):
+        return self.topo.n_local + self.topo.n_halo
+
+    def _barrier(self, buf):
+        if self.on_gpu:
+            self.handles[buf.data_ptr()][0].barrier()
+
+    def _push_input(self, buf):
+        """Halo of the caller's input: one gather kernel per peer into its slots, then the barrier."""
+        t = self.topo
+        P, rank = t.world, t.rank
+        if self.on_gpu:
+            from .ops import gather_rows
+            h, F = self.handles[buf.data_ptr()]
+            for d in range(1, P):
+                q = (rank + d) % P
+                ns = self.hx.send_counts[q]
+                if ns:
+                    peer = h.get_buffer(q, (self.rows_alloc, F), torch.float32)
+                    gather_rows(buf[: t.n_local], self.hx.send_idx[self.soffs[q]: self.soffs[q] + ns],
+                                peer[self.dst_off[q]: self.dst_off[q] + ns])
+            self._barrier(buf)
+        else:
+            self._apply_push_lists_cpu(buf)
+
+    def _apply_push_lists_cpu(self, buf):
+        """gloo stand-in for the in-kernel stores: ship (slot, row) pairs peer by peer."""
+        t = self.topo
+        P, rank = t.world, t.rank
+        codes = self.push_code[:-1].to(torch.int64)
+        peer_of, slot_of = codes >> 28, codes & 0x0FFFFFFF
+        ops, keep, recvs = [], [], []
+        for d in range(1, P):
+            q, s = (rank + d) % P, (rank - d) % P
+            m = peer_of == q
+            if int(m.sum()):
+                sl, data = slot_of[m].contiguous(), buf[self.push_rows[m]].contiguous()
+                keep += [sl, data]
+                ops += [dist.P2POp(dist.isend, sl, q, self.group), dist.P2POp(dist.isend, data, q, self.group)]
+            nr = t.recv_counts[s]
+            if nr:
+                rs = torch.empty(nr, dtype=torch.int64)
+                rd = torch.empty((nr, buf.shape[1]), dtype=buf.dtype)
+                recvs.append((rs, rd))
+                ops += [dist.P2POp(dist.irecv, rs, s, self.group), dist.P2POp(dist.irecv, rd, s, self.group)]
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for rs, rd in recvs:
+            buf[rs] = rd
+
+    def transfers_only(self, buf):
+        if self.topo.world > 1:
+            self._push_input(buf)
+
+    def _step(self, src, T, dst, alpha, epi, use_vals, push):
+        if self._step_fn is not None:
+            self._step_fn(self.sub.plan, src, T, dst, alpha, epi, use_vals)
+            if push:
+                self._apply_push_lists_cpu(dst)
+            return
+        from . import _lib
+        lib = _lib.load()
+        F = src.shape[1]
+        plan = self.sub.plan
+        partial = None
+        if plan.n_slots:
+            partial = self.sub._partial.get(F)
+            if partial is None:
+                partial = torch.empty(plan.n_slots * F, dtype=torch.float32, device=src.device)
+                self.sub._partial[F] = partial
+        if push:
+            rc = lib.ppnp_spmm_step_push(plan.struct(), _lib.ptr(src), _lib.ptr(T), _lib.ptr(dst), _lib.ptr(partial), F, F,
+                                         float(alpha), int(epi), int(bool(use_vals)), _lib.ptr(self.push_ptr),
+                                         _lib.ptr(self.push_code), self._bases[dst.data_ptr()], self.topo.world,
+                                         _lib.current_stream())
+        else:
+            rc = lib.ppnp_spmm_step(plan.struct(), _lib.ptr(src), _lib.ptr(T), _lib.ptr(dst), _lib.ptr(partial), F, F,
+                                    float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
+        _lib.check(rc, "ppnp_spmm_step_push")
+
+    def propagate(self, H_ext, Z_ext, S_ext, K, alpha):
+        from . import _lib
+        t = self.topo
+        multi = t.world > 1
+        if multi:
+            self._push_input(H_ext)
+        src = H_ext
+        for k in range(1, K + 1):
+            dst = Z_ext if (K - k) % 2 == 0 else S_ext
+            if K == 1:
+                epi, use_vals = _lib.EPI_PLAIN, True
+            elif k == 1:
+                epi, use_vals = _lib.EPI_Z2Y, True
+            elif k == K:
+                epi, use_vals = _lib.EPI_Y2Z, False
+            else:
+                epi, use_vals = _lib.EPI_Y, False
+            push = multi and k < K
+            self._step(src, H_ext, dst, alpha, epi, use_vals, push)
+            if push:
+                self._barrier(dst)
+            src = dst
+        return Z_ext[: t.n_local]
+
+
 class _SubGraph:
     def __init__(self, plan, step_fn=None):
         self.plan, self._step_fn = plan, step_fn
@@ -781,14 +977,16 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
-    if transport in ("auto", "pipe") and world > 1:
+    if transport in ("auto", "fused") and world > 1:
+        prop = FusedPushPropagation(topo, dinv)
+    elif transport == "pipe" and world > 1:
         prop = PipelinedPushPropagation(topo, dinv, row_groups=row_groups)
     else:
-        prop = PartitionedPropagation(topo, dinv, phases=phases, transport=("p2p" if transport == "pipe" else transport))
+        prop = PartitionedPropagation(topo, dinv, phases=phases, transport=("p2p" if transport in ("pipe", "fused") else transport))
     del dinv
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
-    H, G, Z, S = (prop.alloc(F, 4) if isinstance(prop, PipelinedPushPropagation) else prop.transport.alloc(F, 4))
+    H, G, Z, S = (prop.alloc(F, 4) if isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation)) else prop.transport.alloc(F, 4))
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     for b in (H, G, Z, S):
         b.zero_()
@@ -853,7 +1051,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     from . import _lib as _l
 
     def transfers_only():
-        if isinstance(prop, PipelinedPushPropagation):
+        if isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation)):
             if world > 1:
                 prop.transfers_only(Z)
             return
@@ -866,7 +1064,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         first = True
         for p in prop.plans:
             if p is not None:
-                acc_pass = (not first) and not isinstance(prop, PipelinedPushPropagation)
+                acc_pass = (not first) and not isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation))
                 p.step(Z, S if acc_pass else H, S, alpha, _l.EPI_Y | (_l.EPI_ACC if acc_pass else 0), False)
             first = False
     ms_compute = timed(compute_only)
@@ -879,7 +1077,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         transfers_only()
     b_.record(); torch.cuda.synchronize()
     my_xfer_us = int(a_.elapsed_time(b_) / 4 * 1e3)
-    hx = prop.hx if isinstance(prop, PipelinedPushPropagation) else getattr(prop.transport, "hx", None)
+    hx = prop.hx if isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation)) else getattr(prop.transport, "hx", None)
     sent_rows = sum(hx.send_counts) if hx is not None else 0
     stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum()), sent_rows, my_xfer_us], dtype=torch.int64, device=dev)
     allstats = [torch.empty_like(stats) for _ in range(world)]
@@ -890,8 +1088,8 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         if p is not None:
             launches += 2 if p.plan.n_fix > 0 else 1
     launches += (world - 1) if prop.transport_name in ("pull", "push") else 0
-    if isinstance(prop, PipelinedPushPropagation):
-        launches += (world - 1) * prop.G
+    if isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation)):
+        launches += (world - 1) * getattr(prop, "G", 0)
     work = 2 * K * nnz * F
     return {
         "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,

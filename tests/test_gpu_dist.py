@@ -26,7 +26,9 @@ def worker(rank, world, port, mode, outdir):
         dinv = pd.global_dinv(indptr, bounds, rank, world, dev)
         topo = pd.build_shard_topology(indptr, cols, bounds, rank)
         phases, transport = mode.split("/")
-        if transport == "pipe":
+        if transport == "fused":
+            prop = pd.FusedPushPropagation(topo, dinv)
+        elif transport == "pipe":
             prop = pd.PipelinedPushPropagation(topo, dinv, row_groups=int(phases))
         else:
             prop = pd.PartitionedPropagation(topo, dinv, phases=phases, transport=transport)
@@ -36,7 +38,7 @@ def worker(rank, world, port, mode, outdir):
         old_of_new = np.argsort(new_of_old)
         mine = old_of_new[lo:hi]
         Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
-        H, Z, S = prop.alloc(F, 3) if transport == "pipe" else prop.transport.alloc(F, 3)
+        H, Z, S = prop.alloc(F, 3) if transport in ("pipe", "fused") else prop.transport.alloc(F, 3)
         H.zero_()
         H[: topo.n_local] = torch.from_numpy(Hg[mine]).to(dev)
         out = prop.propagate(H, Z, S, K, alpha).cpu().numpy()
@@ -53,7 +55,7 @@ def worker(rank, world, port, mode, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["4/pipe", "1/pipe", "two/push", "one/push", "peer/pull", "peer/p2p", "one/p2p"])
+@pytest.mark.parametrize("mode", ["x/fused", "4/pipe", "1/pipe", "two/push", "one/push", "peer/pull", "peer/p2p", "one/p2p"])
 def test_partitioned_matches_oracle_on_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
