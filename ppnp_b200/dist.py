@@ -30,6 +30,28 @@ import torch
 import torch.distributed as dist
 
 
+# ------------------------------------------------------------------------------ rank barrier
+_FLAGS = {}
+
+
+def rank_barrier(handle, device, group=None):
+    """Stream-ordered barrier across the ranks between two propagation steps: everything enqueued on
+    the current stream before it (kernels that stored into peers' memory included) has completed on
+    EVERY rank before anything enqueued after it starts.  Default: a 4-byte NCCL all-reduce (measured
+    correct for the in-kernel peer stores); PPNP_DIST_BARRIER=symm uses the symmetric-memory signal
+    barrier instead (faster, but it let a rank run ahead in the fused-push tests on 2 GPUs)."""
+    import os
+    if os.environ.get("PPNP_DIST_BARRIER", "nccl") == "symm" and handle is not None:
+        handle.barrier()
+        return
+    key = (device, id(group))
+    flag = _FLAGS.get(key)
+    if flag is None:
+        flag = torch.zeros(1, device=device)
+        _FLAGS[key] = flag
+    dist.all_reduce(flag, group=group)
+
+
 # ------------------------------------------------------------------------------ partitioning
 def balanced_row_blocks(weights, world):
     """Boundaries lo_0=0 <= ... <= lo_world=n such that every block carries ~1/world of the weight
@@ -172,7 +194,7 @@ class PeerPull:
         return bufs
 
     def step_barrier(self, buf):
-        self.handles[buf.data_ptr()][0].barrier()
+        rank_barrier(self.handles[buf.data_ptr()][0], buf.device, self.group)
 
     def fetch(self, src, owner):
         """Pull owner's rows of ``src`` (the same symmetric buffer on every rank) into my halo region."""
@@ -242,7 +264,7 @@ class PeerPush:
             peer = h.get_buffer(q, (self.rows_alloc, F), torch.float32)
             ids = self.hx.send_idx[self.soffs[q]: self.soffs[q] + ns]
             gather_rows(src[: t.n_local], ids, peer[self.dst_off[q]: self.dst_off[q] + ns])
-        h.barrier()
+        rank_barrier(h, src.device, self.group)
 
 
 class RoundSendRecv:
@@ -585,7 +607,7 @@ class PipelinedPushPropagation:
 
     def _barrier(self, buf):
         if self.on_gpu:
-            self.handles[buf.data_ptr()][0].barrier()
+            rank_barrier(self.handles[buf.data_ptr()][0], buf.device, self.group)
 
     def transfers_only(self, buf):
         for g in range(self.G):
@@ -739,8 +761,9 @@ class FusedPushPropagation:
         return self.topo.n_local + self.topo.n_halo
 
     def _barrier(self, buf):
-        if self.on_gpu:
-            self.handles[buf.data_ptr()][0].barrier()
+        if not self.on_gpu:
+            return
+        rank_barrier(self.handles[buf.data_ptr()][0], buf.device, self.group)
 
     def _push_input(self, buf):
         """Halo of the caller's input: one gather kernel per peer into its slots, then the barrier."""
