@@ -60,7 +60,6 @@ __device__ __forceinline__ void push_row(const Vec<VEC>& o, int row, int ld, int
         const int code = __ldg(pa->code + i);
         o.store(pa->base[(code >> 28) & (PPNP_MAX_PEERS - 1)] + (int64_t)(code & 0x0fffffff) * ld + f);
     }
-    if (e > b) __threadfence_system();   // peer stores must be performed before this grid is seen as finished
 }
 
 template <typename V, bool COHERENT>
