@@ -121,12 +121,15 @@ int ppnp_spmm_step(const ppnp_plan_t* plan, const float* Zin, const float* T, fl
  * the single-process reference): every finished row r with push_ptr[r] < push_ptr[r+1] is also
  * written to peer_bases[code >> 28] + (code & 0x0fffffff) * ld for code in push_code[push_ptr[r] ..
  * push_ptr[r+1]) -- the halo slots of that row in the peers' mappings (NVLink peer memory) of the
- * output buffer.  peer_bases_host is a HOST array of n_peers device pointers.  The caller orders
+ * output buffer.  push_first[r] summarises the list (-1: none, >= 0: the single code, <= -2: several)
+ * so that the common one-destination case needs no list walk.  peer_bases_host is a HOST array of
+ * n_peers device pointers.  The caller orders
  * the next step after these writes with a barrier across the ranks. */
 int ppnp_spmm_step_push(const ppnp_plan_t* plan, const float* Zin, const float* T, float* Zout,
                         float* partial, int64_t ld, int32_t F, float alpha, int32_t epi,
                         int32_t use_vals, const int32_t* push_ptr, const int32_t* push_code,
-                        const void* const* peer_bases_host, int32_t n_peers, void* stream);
+                        const int32_t* push_first, const void* const* peer_bases_host, int32_t n_peers,
+                        void* stream);
 
 /* K steps from Z_0 = H.  mode PPNP_MODE_SYM: value-free Y-space iteration when plan->vals is
  * given only for the first step (use_vals == 0), stored values every step when use_vals != 0.

@@ -39,7 +39,7 @@ SIGNATURES = {
     "ppnp_csr_normalize_workspace_bytes": (_i64, [_i64]),
     "ppnp_csr_normalize": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ppnp_spmm_step": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _f32, _i32, _i32, _p]),
-    "ppnp_spmm_step_push": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _f32, _i32, _i32, _p, _p, _p, _i32, _p]),
+    "ppnp_spmm_step_push": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _f32, _i32, _i32, _p, _p, _p, _p, _i32, _p]),
     "ppnp_appnp_propagate": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32, _f32, _i32, _i32, _p]),
     "ppnp_appnp_propagate_persistent": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32, _f32, _p]),
     "ppnp_ppr_dense": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),

@@ -50,8 +50,14 @@ constexpr unsigned FULL = 0xffffffffu;
 struct PushArgs {
     const int32_t* ptr;    // [n + 1] per-row ranges into code[], or nullptr (no pushes)
     const int32_t* code;
+    const int32_t* first;  // [n] -1: row is not pushed; >= 0: its only destination code; <= -2: several, use ptr/code
     float* base[PPNP_MAX_PEERS];
 };
+
+template <int VEC>
+__device__ __forceinline__ void push_one(const Vec<VEC>& o, int code, int ld, int f, const PushArgs* pa) {
+    o.store(pa->base[(code >> 28) & (PPNP_MAX_PEERS - 1)] + (int64_t)(code & 0x0fffffff) * ld + f);
+}
 
 template <int VEC>
 __device__ __forceinline__ void push_row(const Vec<VEC>& o, int row, int ld, int f, const PushArgs* pa) {
@@ -72,7 +78,7 @@ template <int VEC>
 __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t, int sv, float deg, bool active,
                                           float* Zout, float* __restrict__ partial, int ld, int f,
                                           float alpha, int epi, const float* __restrict__ row_deg,
-                                          const PushArgs* pa) {
+                                          const PushArgs* pa, int pf) {
     if (!active) return;
     if (sv < 0) {
         acc.store(partial + (int64_t)(sv & 0x7fffffff) * ld + f);
@@ -82,7 +88,8 @@ __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t
         epi_coef(epi, alpha, deg, a, bb);
         const Vec<VEC> o = Vec<VEC>::axpby(a, acc, bb, t);
         o.store_stream(Zout + (int64_t)sv * ld + f);
-        if (pa->ptr != nullptr) push_row<VEC>(o, sv, ld, f, pa);
+        if (pf >= 0) push_one<VEC>(o, pf, ld, f, pa);          // the common case: one peer wants this row
+        else if (pf < -1) push_row<VEC>(o, sv, ld, f, pa);     // several peers
     }
 }
 
@@ -274,13 +281,15 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
                     } else {
                         // ---- general path: some of these edges finish a segment
                         V v[U], t[U];
-                        int ru[U], sv[U];
+                        int ru[U], sv[U], pf[U];
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
                             ru[u] = __shfl_sync(FULL, raw0[r], u0 + u, G);
                             sv[u] = __shfl_sync(FULL, segv0[r], u0 + u, G);
                             v[u].zero();
                             t[u].zero();
+                            pf[u] = -1;
+                            if (pa->first != nullptr && ru[u] < 0 && sv[u] >= 0) pf[u] = __ldg(pa->first + sv[u]);
                             if (active) v[u] = gather_load<V, COHERENT>(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)(ru[u] & 0x7fffffff) * row_bytes));
                             if (active && ru[u] < 0 && sv[u] >= 0) t[u] = V::load_stream(reinterpret_cast<const float*>(tbase + (uint64_t)(unsigned)sv[u] * row_bytes));
                         }
@@ -291,7 +300,7 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
                                 const int pos = j * SE + r * G + u0 + u;
                                 {   // copies: the out-of-line call takes references, acc itself must stay in registers
                                     const V a2 = acc, t2 = t[u];
-                                    emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi, row_deg, pa);
+                                    emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi, row_deg, pa, pf[u]);
                                 }
                                 acc.zero();
                                 seg_begin = pos + 1;
@@ -379,7 +388,7 @@ appnp_persistent_kernel(const int32_t* __restrict__ cols, const float* __restric
                         const float* H, float* Z, float* S, float* partial, int ld, int F, int K, float alpha) {
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     __shared__ PushArgs no_push;
-    if (threadIdx.x == 0) no_push.ptr = nullptr;
+    if (threadIdx.x == 0) { no_push.ptr = nullptr; no_push.first = nullptr; }
     __syncthreads();
     const float* src = H;
     for (int k = 1; k <= K; ++k) {
@@ -610,7 +619,8 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
 
 int ppnp_spmm_step_push(const ppnp_plan_t* plan, const float* Zin, const float* T, float* Zout, float* partial,
                         int64_t ld, int32_t F, float alpha, int32_t epi, int32_t use_vals, const int32_t* push_ptr,
-                        const int32_t* push_code, const void* const* peer_bases_host, int32_t n_peers, void* stream) {
+                        const int32_t* push_code, const int32_t* push_first, const void* const* peer_bases_host,
+                        int32_t n_peers, void* stream) {
     using namespace ppnp;
     int rc = validate_plan(plan);
     if (rc) return rc;
@@ -620,11 +630,12 @@ int ppnp_spmm_step_push(const ppnp_plan_t* plan, const float* Zin, const float* 
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
     PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~31) == 0, "bad epilogue");
-    PPNP_REQUIRE(push_ptr == nullptr || (push_code && peer_bases_host && n_peers >= 1 && n_peers <= PPNP_MAX_PEERS),
-                 "push lists need codes and 1..PPNP_MAX_PEERS peer base pointers");
+    PPNP_REQUIRE(push_ptr == nullptr || (push_code && push_first && peer_bases_host && n_peers >= 1 && n_peers <= PPNP_MAX_PEERS),
+                 "push lists need codes, the per-row summary and 1..PPNP_MAX_PEERS peer base pointers");
     PushArgs pa{};
     pa.ptr = push_ptr;
     pa.code = push_code;
+    pa.first = push_ptr ? push_first : nullptr;
     for (int i = 0; i < PPNP_MAX_PEERS; ++i)
         pa.base[i] = (push_ptr && i < n_peers) ? reinterpret_cast<float*>(const_cast<void*>(peer_bases_host[i])) : nullptr;
     return dispatch_step(plan, Zin, T, Zout, partial, ld, F, alpha, epi, use_vals != 0, pa, as_stream(stream));

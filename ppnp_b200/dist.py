@@ -734,6 +734,14 @@ class FusedPushPropagation:
         self.push_ptr = pp.to(torch.int32).contiguous()
         self.push_code = torch.cat([codes, torch.zeros(1, dtype=torch.int64, device=dev)]).to(torch.int32).contiguous()
         self.push_rows = rows                                     # (CPU emulation)
+        # per-row summary: -1 none, >= 0 the only destination, <= -2 several (walk the list)
+        first = torch.full((n_local,), -1, dtype=torch.int64, device=dev)
+        if rows.numel():
+            one = cnt == 1
+            start = pp[:-1]
+            first[one] = codes[start[one]]
+            first[cnt > 1] = -2
+        self.push_first = first.to(torch.int32).contiguous()
         self.handles, self._bases = {}, {}
         self._C = C
         self.transport_name = "fused-push" if self.on_gpu else "fused-p2p"
@@ -832,7 +840,8 @@ class FusedPushPropagation:
         if push:
             rc = lib.ppnp_spmm_step_push(plan.struct(), _lib.ptr(src), _lib.ptr(T), _lib.ptr(dst), _lib.ptr(partial), F, F,
                                          float(alpha), int(epi), int(bool(use_vals)), _lib.ptr(self.push_ptr),
-                                         _lib.ptr(self.push_code), self._bases[dst.data_ptr()], self.topo.world,
+                                         _lib.ptr(self.push_code), _lib.ptr(self.push_first), self._bases[dst.data_ptr()],
+                                         self.topo.world,
                                          _lib.current_stream())
         else:
             rc = lib.ppnp_spmm_step(plan.struct(), _lib.ptr(src), _lib.ptr(T), _lib.ptr(dst), _lib.ptr(partial), F, F,
