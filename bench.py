@@ -113,6 +113,15 @@ def measured_traffic(key):
     return None, None
 
 
+def n1_reference(wl):
+    """T_1 of this workload through the same code path (committed measurement, profiles/scaling.json)."""
+    p = os.path.join(ROOT, "profiles", "scaling.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(wl)
+    return None
+
+
 def algorithmic_bytes_per_pass(n, nnz, F, value_free=True):
     """per SpMM+axpy step 4(n+1) [indptr] + 4 nnz [indices] (+ 4 nnz [values]) +
     12 n F [read Z once, read H, write Z'].  A pass = 2 x K steps; the value-free iteration still
@@ -242,7 +251,7 @@ def run_ours(args):
                              "unit": "GB/s", "frac": bytes_pass / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None,
                              "peak_source": peak_src + f" x {world} GPUs", "kernel": "spmm_stream_kernel"},
                 "e2e": result.pop("e2e"), "gpu_launches": result.pop("gpu_launches"), "clocks": sampler_clocks,
-                "extra": result,
+                "extra": dict(result, n1_same_workload=n1_reference(wl)),
             }
             print(json.dumps(line))
         dist.barrier()
