@@ -74,7 +74,7 @@ __device__ __forceinline__ V gather_load(const float* p) {
     return V::load(p);
 }
 
-template <int VEC>
+template <int VEC, bool PUSH>
 __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t, int sv, float deg, bool active,
                                           float* Zout, float* __restrict__ partial, int ld, int f,
                                           float alpha, int epi, const float* __restrict__ row_deg,
@@ -88,8 +88,10 @@ __device__ __noinline__ void emit_segment(const Vec<VEC>& acc, const Vec<VEC>& t
         epi_coef(epi, alpha, deg, a, bb);
         const Vec<VEC> o = Vec<VEC>::axpby(a, acc, bb, t);
         o.store_stream(Zout + (int64_t)sv * ld + f);
-        if (pf >= 0) push_one<VEC>(o, pf, ld, f, pa);          // the common case: one peer wants this row
-        else if (pf < -1) push_row<VEC>(o, sv, ld, f, pa);     // several peers
+        if (PUSH) {
+            if (pf >= 0) push_one<VEC>(o, pf, ld, f, pa);          // the common case: one peer wants this row
+            else if (pf < -1) push_row<VEC>(o, sv, ld, f, pa);     // several peers
+        }
     }
 }
 
@@ -122,7 +124,7 @@ struct StageCfg {
 
 // COHERENT: gathers bypass L1 (ld.global.cg).  Needed when the source was written earlier in the SAME
 // launch (persistent K-step kernel): ld.global.nc / L1 hits could return the previous iterate.
-template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE, bool COHERENT>
+template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE, bool COHERENT, bool PUSH>
 __device__ __forceinline__ void
 spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ vals,
                  const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
@@ -289,7 +291,7 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
                             v[u].zero();
                             t[u].zero();
                             pf[u] = -1;
-                            if (pa->first != nullptr && ru[u] < 0 && sv[u] >= 0) pf[u] = __ldg(pa->first + sv[u]);
+                            if (PUSH && ru[u] < 0 && sv[u] >= 0) pf[u] = __ldg(pa->first + sv[u]);
                             if (active) v[u] = gather_load<V, COHERENT>(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)(ru[u] & 0x7fffffff) * row_bytes));
                             if (active && ru[u] < 0 && sv[u] >= 0) t[u] = V::load_stream(reinterpret_cast<const float*>(tbase + (uint64_t)(unsigned)sv[u] * row_bytes));
                         }
@@ -300,7 +302,7 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
                                 const int pos = j * SE + r * G + u0 + u;
                                 {   // copies: the out-of-line call takes references, acc itself must stay in registers
                                     const V a2 = acc, t2 = t[u];
-                                    emit_segment<VEC>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi, row_deg, pa, pf[u]);
+                                    emit_segment<VEC, PUSH>(a2, t2, sv[u], (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi, row_deg, pa, pf[u]);
                                 }
                                 acc.zero();
                                 seg_begin = pos + 1;
@@ -315,14 +317,14 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
     }
 }
 
-template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE>
+template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE, bool PUSH>
 __global__ void __launch_bounds__(256, (G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOCKS : PPNP_SPMM_MINBLOCKS_WIDE)
 spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
                    const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
                    int64_t n_chunks, int chunk_edges, const float* Zin, const float* T, float* Zout,
                    float* partial, int ld, int F, float alpha, int epi, const float* __restrict__ row_deg,
                    const __grid_constant__ PushArgs pa) {
-    spmm_stream_body<VEC, G, HAS_VAL, U, FULL_TILE, false>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, Zin, T,
+    spmm_stream_body<VEC, G, HAS_VAL, U, FULL_TILE, false, PUSH>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, Zin, T,
                                                            Zout, partial, ld, F, alpha, epi, row_deg, &pa);
 }
 
@@ -393,7 +395,7 @@ appnp_persistent_kernel(const int32_t* __restrict__ cols, const float* __restric
     const float* src = H;
     for (int k = 1; k <= K; ++k) {
         float* dst = ((K - k) % 2 == 0) ? Z : S;
-        spmm_stream_body<VEC, G, true, U, FULL_TILE, true>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, src, H,
+        spmm_stream_body<VEC, G, true, U, FULL_TILE, true, false>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, src, H,
                                                             dst, partial, ld, F, alpha, PPNP_EPI_PLAIN, nullptr, &no_push);
         if (n_fix > 0) {
             grid.sync();
@@ -426,9 +428,9 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
     const int64_t groups_per_block = (THREADS / 32) * GPW;
     const int64_t need = (p->n_chunks + groups_per_block - 1) / groups_per_block;
     const bool full_tile = (tiles * G * VEC == F);
-#define PPNP_LAUNCH(HV_, FT_)                                                                                      \
+#define PPNP_LAUNCH2(HV_, FT_, PU_)                                                                                \
     do {                                                                                                           \
-        auto k = spmm_stream_kernel<VEC, G, HV_, U, FT_>;                                                          \
+        auto k = spmm_stream_kernel<VEC, G, HV_, U, FT_, PU_>;                                                     \
         static thread_local int occ = 0;                                                                           \
         const int smem_bytes = StageCfg<G>::words_per_thread(HV_) * THREADS * 4;                                   \
         if (!occ) occ = blocks_per_sm(k, THREADS, smem_bytes);                                                     \
@@ -437,9 +439,11 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
         k<<<grid, THREADS, smem_bytes, stream>>>(p->cols, HV_ ? p->vals : nullptr, p->seg_row, p->chunk_seg, p->n_chunks, \
                                         p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi, p->row_deg, pa); \
     } while (0)
+#define PPNP_LAUNCH(HV_, FT_) do { if (pa.ptr != nullptr) PPNP_LAUNCH2(HV_, FT_, true); else PPNP_LAUNCH2(HV_, FT_, false); } while (0)
     if (use_vals) { if (full_tile) PPNP_LAUNCH(true, true); else PPNP_LAUNCH(true, false); }
     else          { if (full_tile) PPNP_LAUNCH(false, true); else PPNP_LAUNCH(false, false); }
 #undef PPNP_LAUNCH
+#undef PPNP_LAUNCH2
     PPNP_CHECK_LAUNCH("spmm_stream_kernel");
     if (p->n_fix > 0) {
         const int64_t needf = (p->n_fix + groups_per_block - 1) / groups_per_block;
