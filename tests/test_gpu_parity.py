@@ -345,3 +345,65 @@ def test_persistent_kernel_on_hub_rows():
     ref = oracle.c_appnp_f64(oip, oidx, oval, Hn.astype(np.float64), 10, 0.1)
     Z = P.appnp_propagate_persistent(graph, torch.from_numpy(Hn).to(dev()), 10, 0.1)
     assert relerr(Z.cpu().numpy(), ref) < 1e-5
+
+
+# ------------------------------------------------------------------ edge cases and error behaviour
+def _tiny_graph(n_edges_dir, n):
+    import scipy.sparse as sp_
+    rng = np.random.RandomState(n)
+    r = rng.randint(0, n, n_edges_dir); c = rng.randint(0, n, n_edges_dir)
+    keep = r != c
+    a = sp_.csr_matrix((np.ones(keep.sum(), np.float32), (r[keep], c[keep])), shape=(n, n))
+    a = ((a + a.T) > 0).astype(np.float32).tocsr()
+    a.sort_indices()
+    return a
+
+
+@pytest.mark.parametrize("n,m", [(1, 0), (2, 1), (3, 0), (33, 40), (257, 300)])
+def test_tiny_and_edgeless_graphs(n, m):
+    """n = 1, isolated nodes only, graphs far smaller than one chunk: every row is just its self loop or
+    a handful of edges, the stream is almost all padding."""
+    import ppnp_b200 as P
+    adj = _tiny_graph(max(m, 1), n) if m else __import__("scipy.sparse").sparse.csr_matrix((n, n), dtype=np.float32)
+    A = oracle.calc_A_hat(adj, "sym")
+    ahat = P.csr_normalize(torch.from_numpy(adj.indptr.astype(np.int32)).to(dev()),
+                           torch.from_numpy(adj.indices.astype(np.int32)).to(dev()), want_val64=True)
+    assert np.array_equal(ahat.indptr.cpu().numpy(), A.indptr) and np.array_equal(ahat.indices.cpu().numpy(), A.indices)
+    assert np.array_equal(ahat.val64.cpu().numpy(), A.data)
+    Hn = np.random.RandomState(1).randn(n, 5).astype(np.float32)
+    for order in ("natural", "degree"):
+        graph = P.PropagationGraph(ahat, chunk_edges=128, order=order)
+        for K in (1, 3):
+            for use_vals in (False, True):
+                Z = P.appnp_propagate(graph, torch.from_numpy(Hn).to(dev()), K, 0.1, use_vals=use_vals).cpu().numpy()
+                assert relerr(Z, oracle.appnp(A, Hn.astype(np.float64), 0.1, K)) < 1e-5
+    Pi = P.ppr_dense(ahat, 0.1, tol=1e-7).cpu().numpy()
+    assert relerr(Pi, oracle.compute_ppr(adj, 0.1)) < 1e-5
+
+
+def test_argument_errors_are_reported_not_crashes():
+    import ppnp_b200 as P
+    from ppnp_b200 import _lib
+    ahat, adj = gpu_ahat("citeseer")
+    graph = P.PropagationGraph(ahat, chunk_edges=128)
+    n = adj.shape[0]
+    H = torch.randn(n, 4, device=dev())
+    with pytest.raises(ValueError):
+        P.appnp_propagate(graph, torch.randn(n + 1, 4, device=dev()), 3, 0.1)          # wrong number of rows
+    with pytest.raises(ValueError):
+        P.appnp_propagate(graph, H.double(), 3, 0.1)                                    # wrong dtype
+    with pytest.raises(RuntimeError, match="alias"):
+        P.spmm_step(graph, H, H, 0.1, out=H)                                            # in-place step
+    with pytest.raises(RuntimeError, match="epilogue"):
+        P.spmm_step(graph, H, H, 0.1, epi=9)
+    assert torch.equal(P.appnp_propagate(graph, H, 0, 0.1), H)                          # K = 0: Z_0 = H
+    with pytest.raises(ValueError):
+        P.PropagationGraph(ahat, chunk_edges=100)                                       # not a multiple of 128
+    Pi = torch.rand(50, 50, device=dev())
+    with pytest.raises(ValueError):
+        P.gather_gemm(Pi, torch.randn(49, 3, device=dev()))                             # inner dimensions differ
+    with pytest.raises(RuntimeError, match="multiple of 8"):
+        P.gather_gemm_bf16(Pi.to(torch.bfloat16), torch.randn(50, 3, device=dev()))    # unpadded bf16 rows
+    assert P.gather_gemm(Pi, torch.randn(50, 3, device=dev()), torch.zeros(0, dtype=torch.int64, device=dev())).shape == (0, 3)
+    # the message of the last failure is retrievable through the C ABI
+    assert b"multiple of 8" in _lib.load().ppnp_last_error()
