@@ -304,23 +304,60 @@ def run_ours(args):
     dHh = torch.empty((n, F), dtype=torch.float32, pin_memory=True)
     Hd, Gd = torch.empty_like(H), torch.empty_like(G)
 
+    # copy-in, compute and copy-out on three streams: the H2D of G rides under the forward propagation,
+    # the D2H of Z under the backward one, and consecutive passes pipeline (PCIe is full duplex)
+    s_in, s_out, cur = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+    last = {"fwd": None, "bwd": None, "z": None, "dh": None}
+
     def one_pass_e2e():
-        Hd.copy_(Hh, non_blocking=True)
+        with torch.cuda.stream(s_in):
+            if last["fwd"] is not None:
+                s_in.wait_event(last["fwd"])          # Hd is free once the previous forward has consumed it
+            Hd.copy_(Hh, non_blocking=True)
+            eH = torch.cuda.Event(); eH.record(s_in)
+            if last["bwd"] is not None:
+                s_in.wait_event(last["bwd"])
+            Gd.copy_(Gh, non_blocking=True)
+            eG = torch.cuda.Event(); eG.record(s_in)
+        cur.wait_event(eH)
+        if last["z"] is not None:
+            cur.wait_event(last["z"])                 # Z is free once its previous read-back has finished
         P.appnp_propagate(graph, Hd, KSTEPS, ALPHA, use_vals=args.use_vals, out=Z, scratch=scratch)
-        Zh.copy_(Z, non_blocking=True)
-        Gd.copy_(Gh, non_blocking=True)
+        f = torch.cuda.Event(); f.record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(f)
+            Zh.copy_(Z, non_blocking=True)
+            zo = torch.cuda.Event(); zo.record(s_out)
+        cur.wait_event(eG)
+        if last["dh"] is not None:
+            cur.wait_event(last["dh"])
         P.appnp_propagate(graph, Gd, KSTEPS, ALPHA, use_vals=args.use_vals, out=dH, scratch=scratch)
-        dHh.copy_(dH, non_blocking=True)
+        b = torch.cuda.Event(); b.record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(b)
+            dHh.copy_(dH, non_blocking=True)
+            do = torch.cuda.Event(); do.record(s_out)
+        last.update(fwd=f, bwd=b, z=zo, dh=do)
+
+    def drain():
+        cur.wait_stream(s_in)
+        cur.wait_stream(s_out)
 
     one_pass_e2e()
+    drain()
     torch.cuda.synchronize()
+    e2e_steps = max(e2e_steps, 4)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
     e0.record()
     for _ in range(e2e_steps):
         one_pass_e2e()
+    drain()
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1) / e2e_steps
+    assert torch.equal(Zh, Z.cpu()) and torch.equal(dHh, dH.cpu())      # the results did reach the host
 
     # ---- CPU baseline beside it (rank 0, bounded sample)
     cpu = None

@@ -341,23 +341,34 @@ fixup_body(const int32_t* __restrict__ fix_ptr, const int32_t* __restrict__ fix_
     const int g = lane / G;
     const int lg = lane % G;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t total_groups = (((int64_t)gridDim.x * blockDim.x) >> 5) * GPW;
+    const int64_t total_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int f = ((int)blockIdx.y * G + lg) * VEC;
-    if (f < F) {
-        for (int64_t q = warp_global * GPW + g; q < n_fix; q += total_groups) {
-            const int s0 = __ldg(fix_ptr + q), s1 = __ldg(fix_ptr + q + 1);
+    const bool active = f < F;
+    // One WARP per split row: its GPW lane groups add every GPW-th partial (U loads in flight each), a
+    // fixed xor tree over the groups joins them -- a hub row with hundreds of partials is GPW x faster
+    // than one group walking them, and the order of the additions is still fixed (bit-reproducible).
+    for (int64_t q = warp_global; q < n_fix; q += total_warps) {
+        const int s0 = __ldg(fix_ptr + q), s1 = __ldg(fix_ptr + q + 1);
+        V acc; acc.zero();
+        int s = s0 + g;
+        for (; s + (U - 1) * GPW < s1; s += U * GPW) {
+            V p[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                p[u].zero();
+                if (active) p[u] = COHERENT ? V::load_cg(partial + (int64_t)(s + u * GPW) * ld + f) : V::load_plain(partial + (int64_t)(s + u * GPW) * ld + f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc.add(p[u]);
+        }
+        for (; s < s1; s += GPW)
+            if (active) acc.add(COHERENT ? V::load_cg(partial + (int64_t)s * ld + f) : V::load_plain(partial + (int64_t)s * ld + f));
+        __syncwarp();
+#pragma unroll
+        for (int o = G; o < 32; o <<= 1) acc = V::shfl_xor_add(acc, o);
+        if (g == 0 && active) {
             const int row = __ldg(fix_row + q);
             const V t = V::load_stream(T + (int64_t)row * ld + f);
-            V acc; acc.zero();
-            int s = s0;
-            for (; s + U <= s1; s += U) {
-                V p[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) p[u] = COHERENT ? V::load_cg(partial + (int64_t)(s + u) * ld + f) : V::load_plain(partial + (int64_t)(s + u) * ld + f);
-#pragma unroll
-                for (int u = 0; u < U; ++u) acc.add(p[u]);
-            }
-            for (; s < s1; ++s) acc.add(COHERENT ? V::load_cg(partial + (int64_t)s * ld + f) : V::load_plain(partial + (int64_t)s * ld + f));
             float a, bb;
             epi_coef(epi, alpha, __ldg(fix_deg + q), a, bb);
             const V o = V::axpby(a, acc, bb, t);
@@ -446,7 +457,7 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
 #undef PPNP_LAUNCH2
     PPNP_CHECK_LAUNCH("spmm_stream_kernel");
     if (p->n_fix > 0) {
-        const int64_t needf = (p->n_fix + groups_per_block - 1) / groups_per_block;
+        const int64_t needf = (p->n_fix + (THREADS / 32) - 1) / (THREADS / 32);   // one warp per split row
         const int64_t capf = (int64_t)sm_count() * 8;
         dim3 grid((unsigned)(needf < capf ? needf : capf), (unsigned)tiles);
         fixup_kernel<VEC, G><<<grid, THREADS, 0, stream>>>(p->fix_ptr, p->fix_row, p->fix_deg, p->n_fix, partial, T,

@@ -62,6 +62,9 @@ struct Vec<1> {
     __device__ __forceinline__ static Vec axpby(float a, const Vec& u, float b, const Vec& v) {
         Vec r; r.x = fmaf(a, u.x, b * v.x); return r;
     }
+    __device__ __forceinline__ static Vec shfl_xor_add(const Vec& a, int o) {
+        Vec r; r.x = a.x + __shfl_xor_sync(0xffffffffu, a.x, o); return r;
+    }
 };
 template <>
 struct Vec<4> {
@@ -81,6 +84,12 @@ struct Vec<4> {
         Vec r;
         r.v.x = fmaf(a, u.v.x, b * w.v.x); r.v.y = fmaf(a, u.v.y, b * w.v.y);
         r.v.z = fmaf(a, u.v.z, b * w.v.z); r.v.w = fmaf(a, u.v.w, b * w.v.w);
+        return r;
+    }
+    __device__ __forceinline__ static Vec shfl_xor_add(const Vec& a, int o) {
+        Vec r;
+        r.v.x = a.v.x + __shfl_xor_sync(0xffffffffu, a.v.x, o); r.v.y = a.v.y + __shfl_xor_sync(0xffffffffu, a.v.y, o);
+        r.v.z = a.v.z + __shfl_xor_sync(0xffffffffu, a.v.z, o); r.v.w = a.v.w + __shfl_xor_sync(0xffffffffu, a.v.w, o);
         return r;
     }
 };
