@@ -19,7 +19,6 @@ through the public API with pinned HOST buffers, H2D/D2H copies inside the timed
 """
 import argparse
 import json
-import math
 import os
 import sys
 import threading

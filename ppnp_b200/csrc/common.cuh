@@ -35,16 +35,8 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 int sm_count();
 
-// ---- streaming (evict-first) loads / stores: index, teleport and output streams must not
-// ---- push the gathered Z rows out of L2.
-__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
-__device__ __forceinline__ int4 ld_stream(const int4* p) { return __ldcs(p); }
-__device__ __forceinline__ int2 ld_stream(const int2* p) { return __ldcs(p); }
-__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
-__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
-__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
-__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
-
+// Streaming (evict-first) accesses -- __ldcs / __stcs -- are used for index, teleport and output
+// streams so that they do not push the gathered Z rows out of the L2; see Vec<>::load_stream.
 template <int N>
 struct Vec;
 template <>
