@@ -157,6 +157,25 @@ def cpu_port_rate(oracle, n, F, oip, oidx, oval, k_steps, repeats):
     return len(oidx) * F * k_steps / best, best
 
 
+def cpu_torch_sparse_rate(n, F, oip, oidx, oval, k_steps):
+    """edge*feature/s of the literal recurrence with torch.sparse_csr_tensor @ dense on the host cores
+    (the "torch sparse path" north_star mentions; SURVEY.md section 6 measured 4.84e9 on 8 cores)."""
+    import warnings
+    import numpy as np
+    import torch
+    warnings.filterwarnings("ignore", message=".*[Ss]parse.*")
+    A = torch.sparse_csr_tensor(torch.from_numpy(np.ascontiguousarray(oip, dtype=np.int64)),
+                                torch.from_numpy(np.ascontiguousarray(oidx, dtype=np.int64)),
+                                torch.from_numpy(np.ascontiguousarray(oval, dtype=np.float32)), size=(n, n))
+    H = torch.from_numpy(np.random.RandomState(1).randn(n, F).astype(np.float32))
+    Z = H
+    t = time.perf_counter()
+    for _ in range(k_steps):
+        Z = (1 - ALPHA) * (A @ Z) + ALPHA * H
+    dt = time.perf_counter() - t
+    return len(oidx) * F * k_steps / dt, torch.get_num_threads()
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on this box's host cores (the oracle
     port: the reference is pure Python and has no K-step propagation to run)."""
@@ -180,6 +199,7 @@ def run_reference(args):
         t_total += t
     value = sum(rates) / len(rates)
     sample = f"{k_sample} of the 20 propagation steps of one pass per bench step ({wl}, nnz(A_hat)={len(oidx)}, F={F})"
+    ts_rate, ts_threads = cpu_torch_sparse_rate(n, F, oip, oidx, oval, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup if args.warmup is not None else 1,
@@ -187,7 +207,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl, "n": n, "nnz_a_hat": int(len(oidx)), "F": F, "K": KSTEPS, "alpha": ALPHA,
                    "pass": "K=10 forward + K=10 backward (extrapolated from the sample)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "torch_sparse_csr": {"value": ts_rate, "threads": ts_threads, "sample": "1 step"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -369,7 +390,9 @@ def run_ours(args):
         cores = oracle.clib().oracle_num_threads()
         k_sample = 2 if n >= 1_000_000 else 10
         rate, secs = cpu_port_rate(oracle, n, F, oip, oidx, oval, k_sample, 2)
+        ts_rate, ts_threads = cpu_torch_sparse_rate(n, F, oip, oidx, oval, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "torch_sparse_csr": {"value": ts_rate, "threads": ts_threads, "sample": "1 step"},
                "sample": f"{k_sample} of the 20 propagation steps of one pass, same graph and F, fp32 OpenMP C port "
                          f"(oracle/ppnp_oracle.c), best of 2 ({secs:.2f} s)"}
 
