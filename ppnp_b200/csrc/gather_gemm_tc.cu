@@ -280,12 +280,24 @@ inline TcShape tc_shape(int64_t m, int64_t n, int C) {
     s.k_pad = (int64_t)s.kb_total * TC_BK;
     s.m_tiles = (m + TC_BM - 1) / TC_BM;
     s.m_pad = s.m_tiles * TC_BM;
-    int64_t want = (2 * (int64_t)sm_count() + s.m_tiles - 1) / s.m_tiles;   // fill the GPU about twice
-    if (s.m_tiles >= 2 * (int64_t)sm_count()) want = 1;
-    int64_t max_splits = s.kb_total / 8;                                     // at least 8 k-blocks per slice
+    // One CTA per SM is resident (6 stages of smem), so the grid runs in waves of sm_count CTAs: pick the
+    // number of K-slices that wastes the least of the last wave (155 row tiles x 2 slices = 2.09 waves
+    // ran at 70 %; x 19 slices = 19.9 waves).  At least 8 k-blocks per slice keep the pipeline busy.
+    const int64_t sms = sm_count();
+    int64_t max_splits = s.kb_total / 8;
     if (max_splits < 1) max_splits = 1;
-    if (want > max_splits) want = max_splits;
-    if (want < 1) want = 1;
+    if (max_splits > 64) max_splits = 64;
+    int64_t want = 1;
+    double best = -1.0;
+    for (int64_t c = 1; c <= max_splits; ++c) {
+        const int64_t per = (s.kb_total + c - 1) / c;
+        const int64_t real = (s.kb_total + per - 1) / per;          // slices that actually exist
+        const int64_t ctas = s.m_tiles * real;
+        const int64_t waves = (ctas + sms - 1) / sms;
+        // useful fraction of the waves, minus a small charge per slice for the partial-sum traffic
+        const double eff = (double)ctas / (double)(waves * sms) - 0.002 * (double)real;
+        if (eff > best + 1e-9) { best = eff; want = c; }
+    }
     s.kb_per_split = (int)((s.kb_total + want - 1) / want);
     s.splits = (s.kb_total + s.kb_per_split - 1) / s.kb_per_split;
     return s;
