@@ -294,8 +294,10 @@ inline TcShape tc_shape(int64_t m, int64_t n, int C) {
         const int64_t real = (s.kb_total + per - 1) / per;          // slices that actually exist
         const int64_t ctas = s.m_tiles * real;
         const int64_t waves = (ctas + sms - 1) / sms;
-        // useful fraction of the waves, minus a small charge per slice for the partial-sum traffic
-        const double eff = (double)ctas / (double)(waves * sms) - 0.002 * (double)real;
+        // useful fraction of the waves, minus a charge per slice for the partial sums (written by the
+        // epilogue, re-read by the reduce kernel): negligible at N_pad = 16, 0.13 ms of 0.21 at N_pad = 64
+        const double w = (double)s.n_pad / 16.0;
+        const double eff = (double)ctas / (double)(waves * sms) - 0.002 * w * w * (double)real;
         if (eff > best + 1e-9) { best = eff; want = c; }
     }
     s.kb_per_split = (int)((s.kb_total + want - 1) / want);
