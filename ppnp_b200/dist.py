@@ -5,23 +5,29 @@ Rank p owns a contiguous block of rows of A_hat, Z and H.  Row i of Z_{k+1} need
 i's neighbours only, so one exchange per iteration suffices:
 
   * the shard's column ids are remapped to [local rows | halo slots]; halo slots are the distinct
-    remote rows the shard references, grouped by owner and sorted, so the NCCL all-to-all receives
-    straight into the tail of the Z buffer (no unpack);
-  * every step: pack the rows each peer needs (send lists exchanged once at set-up), all_to_all
-    over NVLink, then the same fused SpMM+teleport kernel as on one GPU (csrc/appnp_spmm.cu) over
-    the extended buffer;
-  * rows whose neighbours are all local ("interior") do not depend on the exchange: they are a
-    separate edge stream that runs on the compute stream while the all-to-all is in flight, the
-    boundary rows follow once the halo has landed;
-  * row-block boundaries are chosen by the non-zero prefix sum, not by row count (R-MAT rows are
-    heavily skewed: equal row blocks would put 44 % of the edges on rank 0 of 8).
+    remote rows the shard references, grouped by owner and sorted (``build_shard_topology``);
+  * row-block boundaries are chosen by the non-zero prefix sum of a block-cyclically relabelled id
+    space (``stripe_relabel``, ``balanced_row_blocks``): R-MAT rows are heavily skewed, equal row
+    blocks would put 44 % of the edges on rank 0 of 8, and un-mixed nnz-balanced blocks make the
+    last rank ship 11x the rows of the first;
+  * the exchange itself has several implementations, all driving the same fused SpMM+teleport
+    kernel (csrc/appnp_spmm.cu) over the extended [local | halo] buffer:
+      - ``FusedPushPropagation`` (default on GPUs): the kernel's epilogue stores every finished row
+        that peers reference straight into their halo slots over NVLink peer memory; one 4-byte
+        all-reduce per step is the barrier;
+      - ``PipelinedPushPropagation``: row groups, the rows of a finished group are pushed by a
+        gather kernel on a side stream while the next group computes;
+      - ``PartitionedPropagation``: per-owner / local-remote edge phases with the accumulate
+        epilogue (PPNP_EPI_ACC) over peer pull, owner push, NCCL point-to-point or one all-to-all.
+    profiles/r01_scaling.md has the measurements that ordered them.
 
 The backward pass is the same operator on the upstream gradient (A_hat symmetric), so it uses
-the same partition and halo lists.
+the same partition and the same lists.
 
-Everything here is index bookkeeping plus torch.distributed calls; the arithmetic is in the CUDA
-library.  ``ShardTopology`` and ``HaloExchange`` are device-agnostic so that the host logic is
-tested on CPU with the gloo backend (tests/test_dist_cpu.py).
+Everything here is index bookkeeping plus torch.distributed / symmetric-memory calls; the
+arithmetic is in the CUDA library.  Topology, lists and every orchestration are device-agnostic
+and run on CPU with the gloo backend (tests/test_dist_cpu.py) with a numpy walker of the edge
+stream standing in for the kernel; the package itself has no CPU implementation of the kernel.
 """
 from dataclasses import dataclass
 from typing import List, Optional
@@ -1010,7 +1016,15 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
     if transport in ("auto", "fused") and world > 1:
-        prop = FusedPushPropagation(topo, dinv)
+        try:
+            prop = FusedPushPropagation(topo, dinv)
+            prop.alloc(4, 1)                                  # peer mappings must be obtainable on this box
+        except Exception as e:  # noqa: BLE001
+            if transport == "fused":
+                raise
+            import warnings
+            warnings.warn(f"peer-memory transport unavailable ({type(e).__name__}: {e}); falling back to NCCL point-to-point")
+            prop = PartitionedPropagation(topo, dinv, phases="one", transport="p2p")
     elif transport == "pipe" and world > 1:
         prop = PipelinedPushPropagation(topo, dinv, row_groups=row_groups)
     else:

@@ -111,3 +111,18 @@ def test_balanced_row_blocks_handles_skew():
     sums = [int(w[b[i]:b[i + 1]].sum()) for i in range(4)]
     assert b[0] == 0 and b[-1] == 1000 and max(sums) <= 2 * (int(w.sum()) // 4)
     assert balanced_row_blocks(torch.ones(5), 8)[-1] == 5      # more ranks than rows: empty blocks allowed
+
+
+def test_stripe_relabel_is_a_bijection_that_mixes_the_id_space():
+    from ppnp_b200.dist import auto_stripes, stripe_relabel
+    for n, world in ((204_800, 2), (1_000_000, 8), (100_000, 4)):
+        st = auto_stripes(n, world)
+        assert st >= 1 and (st == 1 or n % (world * st) == 0)
+        f = stripe_relabel(torch.arange(n), n, world, st)
+        assert torch.equal(torch.sort(f).values, torch.arange(n))
+        if st > 1:
+            # the first 1/world of the NEW ids draws evenly from the whole old range
+            old_in_first = torch.nonzero(f < n // world).flatten()
+            assert old_in_first.max() > 0.9 * n and abs(float(old_in_first.float().mean()) / n - 0.5) < 0.1
+    assert auto_stripes(1000, 1) == 1 and auto_stripes(1001, 2) == 1      # nothing to deal / not divisible
+    assert torch.equal(stripe_relabel(torch.arange(10), 10, 1, 4), torch.arange(10))
