@@ -41,6 +41,7 @@ static int lru_touch(lru_t* c, int32_t x) {
     return 1;
 }
 
+static int cmp_i32_local(const int32_t* a, const int32_t* b) { return (*a > *b) - (*a < *b); }
 static int64_t* g_deg;
 static int cmp_deg_desc(const void* a, const void* b) {
     int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
@@ -66,6 +67,7 @@ static void simulate(const char* name, int64_t n, const int64_t* indptr, const i
     printf("%-14s accesses %lld  misses %lld (%.2f%%)  gather DRAM %.3f GB  (compulsory %.3f GB, x%.2f)\n",
            name, (long long)acc, (long long)miss, 100.0 * miss / acc, miss * (double)row_bytes / 1e9,
            comp / 1e9, miss * (double)row_bytes / comp);
+    fflush(stdout);
     free(c.prev); free(c.next); free(c.in);
 }
 
@@ -99,7 +101,7 @@ int main(int argc, char** argv) {
     /* hub-cluster: walk degree-desc; place vertex, then its unplaced neighbours of degree <= T */
     {
         int32_t* by_deg = malloc(n * 4); memcpy(by_deg, order, n * 4);
-        for (int T = 2; T <= 32; T *= 4) {
+        for (int T = 2; T <= 32 && !getenv("L2SIM_FAST"); T *= 4) {
             uint8_t* placed = calloc(n, 1); int64_t p = 0;
             for (int64_t q = 0; q < n; ++q) {
                 const int32_t h = by_deg[q];
@@ -118,32 +120,41 @@ int main(int argc, char** argv) {
     }
 
     /* 2D hub blocking on degree-desc labels: hub rows (top NH by degree) are processed
-       column-block-major (virtual rows -> partials); other rows with the block that holds them. */
+       column-block-major (virtual rows -> partials); other rows with the block that holds them.
+       NH / BS lists come from the environment (L2SIM_NH, L2SIM_BS, comma separated). */
     {
         qsort(order, n, 4, cmp_deg_desc);              /* order[p] = old id with rank p */
         int32_t* rank = malloc(n * 4);
         for (int64_t p = 0; p < n; ++p) rank[order[p]] = (int32_t)p;
-        const int64_t NHs[] = {20000, 50000, 100000, 200000};
-        const int64_t BSs[] = {125000, 250000, 500000};
-        for (int a = 0; a < 4; ++a) for (int bsi = 0; bsi < 3; ++bsi) {
-            const int64_t NH = NHs[a], BS = BSs[bsi];
+        int64_t NHs[8] = {20000, 50000, 100000, 200000}, BSs[8] = {125000, 250000, 500000};
+        int nNH = 4, nBS = 3;
+        const char* e1 = getenv("L2SIM_NH"); const char* e2 = getenv("L2SIM_BS");
+        if (e1) { nNH = 0; char* t = strdup(e1); for (char* q = strtok(t, ","); q && nNH < 8; q = strtok(NULL, ",")) NHs[nNH++] = atoll(q); }
+        if (e2) { nBS = 0; char* t = strdup(e2); for (char* q = strtok(t, ","); q && nBS < 8; q = strtok(NULL, ",")) BSs[nBS++] = atoll(q); }
+        for (int a = 0; a < nNH; ++a) for (int bsi = 0; bsi < nBS; ++bsi) {
+            const int64_t NH = NHs[a] < n ? NHs[a] : n, BS = BSs[bsi];
             const int64_t nb = (n + BS - 1) / BS;
+            /* hub edge lists as column RANKS (self loop included), sorted: one pass per hub, then cursors */
+            int64_t* hp = malloc((NH + 1) * 8); hp[0] = 0;
+            for (int64_t p = 0; p < NH; ++p) hp[p + 1] = hp[p] + (indptr[order[p] + 1] - indptr[order[p]]) + 1;
+            int32_t* hr = malloc(hp[NH] * 4);
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int64_t p = 0; p < NH; ++p) {
+                const int32_t h = order[p]; int64_t o = hp[p];
+                hr[o++] = (int32_t)p;
+                for (int64_t t = indptr[h]; t < indptr[h + 1]; ++t) hr[o++] = rank[indices[t]];
+                qsort(hr + hp[p], hp[p + 1] - hp[p], 4, (int (*)(const void*, const void*))cmp_i32_local);
+            }
+            int64_t* cur = malloc(NH * 8); memcpy(cur, hp, NH * 8);
             lru_t c; lru_init(&c, 4 * n + 2, cap_rows);
             int64_t miss = 0, acc = 0, poll = n, nvirt = 0;
             for (int64_t b = 0; b < nb; ++b) {
                 const int64_t lo = b * BS, hi = (b + 1) * BS < n ? (b + 1) * BS : n;
-                /* hub virtual rows: edges of hub h whose column rank lies in [lo,hi) (self included) */
                 for (int64_t p = 0; p < NH; ++p) {
-                    const int32_t h = order[p];
                     int any = 0;
-                    if (p >= lo && p < hi) { miss += lru_touch(&c, h); acc++; any = 1; }
-                    for (int64_t t = indptr[h]; t < indptr[h + 1]; ++t) {
-                        const int32_t v = indices[t];
-                        if (rank[v] >= lo && rank[v] < hi) { miss += lru_touch(&c, v); acc++; any = 1; }
-                    }
-                    if (any) { nvirt++; if (pollute) lru_touch(&c, (int32_t)poll++); if (poll >= 4 * n) poll = n; }
+                    while (cur[p] < hp[p + 1] && hr[cur[p]] < hi) { miss += lru_touch(&c, order[hr[cur[p]]]); acc++; cur[p]++; any = 1; }
+                    if (any) { nvirt++; if (pollute) { lru_touch(&c, (int32_t)poll++); if (poll >= 4 * n) poll = n; } }
                 }
-                /* non-hub rows living in this block, whole rows */
                 for (int64_t p = (lo > NH ? lo : NH); p < hi; ++p) {
                     const int32_t i = order[p];
                     miss += lru_touch(&c, i); acc++;
@@ -154,10 +165,12 @@ int main(int argc, char** argv) {
             printf("hub2d NH=%lld BS=%lld: accesses %lld misses %lld (%.2f%%) gather DRAM %.3f GB, virt rows %lld (partials %.3f GB w+r)\n",
                    (long long)NH, (long long)BS, (long long)acc, (long long)miss, 100.0 * miss / acc,
                    miss * (double)row_bytes / 1e9, (long long)nvirt, 2.0 * nvirt * row_bytes / 1e9);
-            free(c.prev); free(c.next); free(c.in);
+            fflush(stdout);
+            free(c.prev); free(c.next); free(c.in); free(hp); free(hr); free(cur);
         }
         free(rank);
     }
+
     /* random */
     {
         for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)i;
