@@ -282,7 +282,11 @@ def run_ours(args):
     t0 = time.perf_counter()
     ip, idx = rmat_adjacency(n, raw, scale, seed=0, device=dev)
     ahat = P.csr_normalize(ip, idx)
-    graph = P.PropagationGraph(ahat, chunk_edges=args.chunk_edges, order=args.order)
+    carve = None
+    if args.order == "carve":
+        carve = {"block_cols": args.carve_block_cols, "n_blocks": args.carve_blocks, "min_piece": args.carve_min_piece,
+                 "wide_cta": not args.carve_narrow_cta}
+    graph = P.PropagationGraph(ahat, chunk_edges=args.chunk_edges, order=args.order, idx16=args.idx16, carve=carve)
     nnz = ahat.nnz
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
@@ -404,6 +408,7 @@ def run_ours(args):
                    "pass": "K=10 forward + K=10 backward = 20 fused SpMM+teleport launches",
                    "form": "stored values" if args.use_vals else "value-free Y-space (stored values in step 1)",
                    "order": args.order, "chunk_edges": args.chunk_edges, "l2": "inputs larger than L2 (3 x 512 MB)",
+                   "idx16": bool(args.idx16), "carve": graph.plan.carve,
                    "graph_build_s": round(t_build, 2)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -426,7 +431,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--order", default="degree", choices=["natural", "degree"])
+    ap.add_argument("--order", default="degree", choices=["natural", "degree", "carve"])
+    ap.add_argument("--idx16", action="store_true", help="16-byte staging of a lane-transposed index stream")
+    ap.add_argument("--carve-block-cols", type=int, default=512, help="--order carve: columns per L1-sized block")
+    ap.add_argument("--carve-blocks", type=int, default=64, help="--order carve: number of hot column blocks")
+    ap.add_argument("--carve-min-piece", type=int, default=4, help="--order carve: smallest (row, block) piece taken out of its row")
+    ap.add_argument("--carve-narrow-cta", action="store_true", help="--order carve: keep the 256-thread CTAs")
     ap.add_argument("--chunk-edges", type=int, default=256)
     ap.add_argument("--use-vals", action="store_true", help="stored-value form in every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

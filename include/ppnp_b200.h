@@ -89,6 +89,21 @@ int ppnp_csr_normalize(const int32_t* indptr, const int32_t* indices, const floa
  * values of A_hat in stream order; without them every edge has weight 1 (value-free form,
  * SURVEY.md section 8d) and the row scaling is done by the epilogue from the row degree.
  * ---------------------------------------------------------------------------------------- */
+/* plan->flags.
+ * PPNP_PLAN_WIDE_CTA: launch one 1024-thread CTA per SM instead of four 256-thread ones, so that all
+ *   the warps of an SM walk CONSECUTIVE chunks -- for "carved" streams (plan.py build_carved_plan)
+ *   whose leading part lists, column block by column block, the pieces of rows that fall into an
+ *   L1-sized block of hot columns: the gathered rows of the block are then re-used out of the SM's
+ *   L1 instead of crossing the L2 -> SM fabric once per edge.
+ * PPNP_PLAN_LANE_GROUP(flags) = G > 0: cols (and vals) are stored "lane-transposed" for lane groups
+ *   of G lanes: the 4 index words one lane consumes over 4 / SR consecutive slabs (SR = max(1, 16/G)
+ *   words per lane and slab) are contiguous, so each lane stages them with ONE 16-byte cp.async.
+ *   Stored position of logical chunk position p (slab j = p / SE, word r = (p % SE) / G, lane
+ *   l = p % G, SE = SR * G, CPS = 4 / SR):  (j / CPS) * CPS * SE + l * 4 + (j % CPS) * SR + r.
+ *   A launch whose feature width asks for another group size rejects the plan (PPNP_EINVAL). */
+#define PPNP_PLAN_WIDE_CTA 1
+#define PPNP_PLAN_LANE_GROUP(flags) (((flags) >> 8) & 0xff)
+
 typedef struct ppnp_plan {
     int64_t n;              /* rows                                                     */
     int64_t n_edges;        /* stream length, multiple of chunk_edges                   */
@@ -97,7 +112,7 @@ typedef struct ppnp_plan {
     int64_t n_fix;          /* rows split over several segments                         */
     int64_t n_slots;        /* partial segments                                          */
     int32_t chunk_edges;    /* edges per chunk (multiple of 128)                        */
-    int32_t reserved;
+    int32_t flags;          /* PPNP_PLAN_* bits below; 0 = row-major stream, linear index layout */
     const int32_t* cols;      /* [n_edges]                                              */
     const float* vals;        /* [n_edges] or NULL                                      */
     const int32_t* seg_row;   /* [n_segs + 64] (64 readable spare entries after the last one) */

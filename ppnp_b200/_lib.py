@@ -22,7 +22,7 @@ class PlanStruct(C.Structure):
     """Mirror of ppnp_plan_t."""
     _fields_ = [
         ("n", C.c_int64), ("n_edges", C.c_int64), ("n_chunks", C.c_int64), ("n_segs", C.c_int64),
-        ("n_fix", C.c_int64), ("n_slots", C.c_int64), ("chunk_edges", C.c_int32), ("reserved", C.c_int32),
+        ("n_fix", C.c_int64), ("n_slots", C.c_int64), ("chunk_edges", C.c_int32), ("flags", C.c_int32),
         ("cols", C.c_void_p), ("vals", C.c_void_p), ("seg_row", C.c_void_p), ("chunk_seg", C.c_void_p),
         ("fix_ptr", C.c_void_p), ("fix_row", C.c_void_p), ("fix_deg", C.c_void_p), ("row_deg", C.c_void_p),
     ]

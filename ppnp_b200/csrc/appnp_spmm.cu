@@ -37,6 +37,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef PPNP_SPMM_RING
 #define PPNP_SPMM_RING 8        // gathers kept in flight per lane on the rolling path
 #endif
+#ifndef PPNP_SPMM_SEGPRED
+#define PPNP_SPMM_SEGPRED 0     // 1: only the lanes that end a segment fetch their segment row (4-byte staging path)
+#endif
 #ifndef PPNP_SPMM_U4
 #define PPNP_SPMM_U4 4          // float4 gathers issued back to back per group (VEC == 4)
 #endif
@@ -109,6 +112,10 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {   // L1-bypassing (.cg): 16 B only
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -122,9 +129,26 @@ struct StageCfg {
     static constexpr int words_per_thread(bool has_val) { return SR * (ISLOTS * (has_val ? 2 : 1) + SSLOTS); }
 };
 
+// Lane-transposed streams (PPNP_PLAN_LANE_GROUP, G >= 4): the 4 index words a lane consumes over CPS
+// consecutive slabs (a "quad") are contiguous in memory, so ONE 16-byte cp.async.cg per lane stages
+// them -- a quarter of the copy instructions of the 4-byte form and none of its per-element L1
+// data-pipe wavefronts (profiles/r01_prof_spmm5: LDGSTS.32 staging took a third of the pipe).
+// Schedule (everything issued in iteration j-1 has landed at the top of iteration j):
+//   quad Q (slabs Q*CPS ..) is requested in iteration Q*CPS - 2, read from iteration Q*CPS - 1 (ballot
+//   for the segment rows of its first slab) to (Q+1)*CPS - 1; the ring holds NQ quads;
+//   segment rows of slab j+1 are requested in iteration j, only by the lanes that end a segment.
+template <int G>
+struct Stage16Cfg {
+    static constexpr int SR = (G >= 16) ? 1 : 16 / G;
+    static constexpr int CPS = 4 / SR;                 // slabs per quad
+    static constexpr int NQ = (CPS == 1) ? 4 : 2;      // quads in the ring (slot of Q is free again in iteration Q*CPS - 2)
+    static constexpr int SSL = 2;                      // segment-row slots: slab j (read) and j + 1 (landing)
+    static constexpr int words_per_thread(bool has_val) { return NQ * 4 * (has_val ? 2 : 1) + SSL * SR; }
+};
+
 // COHERENT: gathers bypass L1 (ld.global.cg).  Needed when the source was written earlier in the SAME
 // launch (persistent K-step kernel): ld.global.nc / L1 hits could return the previous iterate.
-template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE, bool COHERENT, bool PUSH>
+template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE, bool COHERENT, bool PUSH, int NT = 256, bool IDX16 = false>
 __device__ __forceinline__ void
 spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ vals,
                  const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
@@ -138,6 +162,9 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
     constexpr int SR = SC::SR;
     constexpr int SE = SR * G;                      // edges per slab
     constexpr int PD = SC::PD, ISLOTS = SC::ISLOTS, SSLOTS = SC::SSLOTS;
+    using S16 = Stage16Cfg<(G >= 4) ? G : 4>;
+    constexpr int CPS = S16::CPS, NQ = S16::NQ, SSL = S16::SSL;
+    static_assert(!IDX16 || G >= 4, "lane-transposed staging needs lane groups of at least 4");
     constexpr int RING = (SE >= PPNP_SPMM_RING) ? PPNP_SPMM_RING : SE;
     static_assert(G % U == 0, "sub-batch must divide the register slab");
     static_assert(SE % RING == 0, "ring must divide the slab");
@@ -145,9 +172,12 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
     // private staging slots, [slot][word r][thread]: conflict-free, no cross-thread visibility needed
     extern __shared__ int32_t stage[];
     const int tid = threadIdx.x;
-    int32_t* s_idx = stage + tid;                                   // + (slot * SR + r) * 256
-    int32_t* s_seg = stage + ISLOTS * SR * 256 + tid;               // + (slot * SR + r) * 256
-    float* s_val = reinterpret_cast<float*>(stage + (ISLOTS + SSLOTS) * SR * 256) + tid;
+    int32_t* s_idx = stage + tid;                                   // + (slot * SR + r) * NT
+    int32_t* s_seg = stage + (IDX16 ? NQ * 4 * (HAS_VAL ? 2 : 1) : ISLOTS * SR) * NT + tid;   // + (slot * SR + r) * NT
+    float* s_val = reinterpret_cast<float*>(stage + (ISLOTS + SSLOTS) * SR * NT) + tid;
+    // IDX16: [quad slot][thread][4 words] for indices, then the same for values, then the segment rows
+    int32_t* s_idx4 = stage + tid * 4;                              // + slot * NT * 4 + word
+    float* s_val4 = reinterpret_cast<float*>(stage + NQ * 4 * NT) + tid * 4;
 
     const int lane = tid & 31;
     const int g = lane / G;
@@ -176,14 +206,37 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
         V acc; acc.zero();
         int seg_begin = 0;  // chunk-local position where the running segment started
 
-        // ---- prologue: indices of slabs 0 .. 2*PD-1, then segment rows of slabs 0 .. PD-1
+        // ---- prologue
+        const int32_t* cp16 = cols + c * (int64_t)chunk_edges + lg * 4;      // IDX16: + quad * CPS * SE
+        const float* vp16 = HAS_VAL ? vals + c * (int64_t)chunk_edges + lg * 4 : nullptr;
+        if constexpr (IDX16) {
+            // quads that iteration 0 (and its look-ahead to slab 1) reads; then the segment rows of slab 0
+#pragma unroll
+            for (int Q = 0; Q * CPS < 2; ++Q) {
+                if (Q * CPS < n_slabs) {
+                    cp_async16(s_idx4 + (Q % NQ) * NT * 4, cp16 + Q * (CPS * SE));
+                    if (HAS_VAL) cp_async16(s_val4 + (Q % NQ) * NT * 4, vp16 + Q * (CPS * SE));
+                }
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+#pragma unroll
+            for (int r = 0; r < SR; ++r) {
+                const int raw = s_idx4[r];                       // quad 0, slab 0, word r
+                const unsigned e = (__ballot_sync(FULL, raw < 0) >> gshift) & gbits;
+                if (raw < 0) cp_async4(s_seg + r * NT, seg_row + s + __popc(e & lt));
+                s += __popc(e);
+            }
+            cp_async_commit();
+        } else {
+        // indices of slabs 0 .. 2*PD-1, then segment rows of slabs 0 .. PD-1
 #pragma unroll
         for (int t = 0; t < 2 * PD; ++t) {
             const int jt = (t < n_slabs) ? t : n_slabs - 1;
 #pragma unroll
             for (int r = 0; r < SR; ++r) {
-                cp_async4(s_idx + ((t % ISLOTS) * SR + r) * 256, cp + jt * SE + r * G);
-                if (HAS_VAL) cp_async4(s_val + ((t % ISLOTS) * SR + r) * 256, vp + jt * SE + r * G);
+                cp_async4(s_idx + ((t % ISLOTS) * SR + r) * NT, cp + jt * SE + r * G);
+                if (HAS_VAL) cp_async4(s_val + ((t % ISLOTS) * SR + r) * NT, vp + jt * SE + r * G);
             }
         }
         cp_async_commit();
@@ -192,18 +245,57 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
         for (int t = 0; t < PD; ++t) {
 #pragma unroll
             for (int r = 0; r < SR; ++r) {
-                const int raw = s_idx[((t % ISLOTS) * SR + r) * 256];
+                const int raw = s_idx[((t % ISLOTS) * SR + r) * NT];
                 unsigned e = (__ballot_sync(FULL, raw < 0) >> gshift) & gbits;
                 if (t >= n_slabs) e = 0;
-                cp_async4(s_seg + ((t % SSLOTS) * SR + r) * 256, seg_row + s + __popc(e & lt));
+                if (!PPNP_SPMM_SEGPRED || raw < 0) cp_async4(s_seg + ((t % SSLOTS) * SR + r) * NT, seg_row + s + __popc(e & lt));
                 s += __popc(e);
             }
         }
         cp_async_commit();
         cp_async_wait<0>();   // slab 0's segment rows are read in the first iteration
+        }
 
 #pragma unroll 1
         for (int j = 0; j < n_slabs; ++j) {
+            int raw0[SR], segv0[SR];
+            float w0[SR];
+            unsigned ends0[SR];
+            unsigned any_end = 0;
+            if constexpr (IDX16) {
+                cp_async_wait<0>();   // indices up to slab j+1 (and the quad requested last time), segment rows of slab j
+                // request: the quad whose first slab is j+2, segment rows of slab j+1
+                if ((j + 2) % CPS == 0 && j + 2 < n_slabs) {
+                    const int Q = (j + 2) / CPS;
+                    cp_async16(s_idx4 + (Q % NQ) * NT * 4, cp16 + Q * (CPS * SE));
+                    if (HAS_VAL) cp_async16(s_val4 + (Q % NQ) * NT * 4, vp16 + Q * (CPS * SE));
+                }
+                {
+                    const int jn = j + 1;
+                    const int32_t* qn = s_idx4 + ((jn / CPS) % NQ) * NT * 4 + (jn % CPS) * SR;
+#pragma unroll
+                    for (int r = 0; r < SR; ++r) {
+                        const int rawn = qn[r];
+                        unsigned e = (__ballot_sync(FULL, rawn < 0) >> gshift) & gbits;
+                        if (jn >= n_slabs) e = 0;          // past the chunk: stale words, never processed
+                        if (rawn < 0 && jn < n_slabs) cp_async4(s_seg + ((jn % SSL) * SR + r) * NT, seg_row + s + __popc(e & lt));
+                        s += __popc(e);
+                    }
+                }
+                cp_async_commit();
+                {
+                    const int32_t* q0 = s_idx4 + ((j / CPS) % NQ) * NT * 4 + (j % CPS) * SR;
+                    const float* v0 = s_val4 + ((j / CPS) % NQ) * NT * 4 + (j % CPS) * SR;
+#pragma unroll
+                    for (int r = 0; r < SR; ++r) {
+                        raw0[r] = q0[r];
+                        segv0[r] = s_seg[((j % SSL) * SR + r) * NT];
+                        if (HAS_VAL) w0[r] = v0[r];
+                        ends0[r] = (__ballot_sync(FULL, raw0[r] < 0) >> gshift) & gbits;
+                        any_end |= ends0[r];
+                    }
+                }
+            } else {
             // everything but the PD-1 newest groups has landed: indices up to slab j+PD, segment rows up to slab j
             cp_async_wait<PD - 1>();
             // request: indices of slab j+2PD, segment rows of slab j+PD
@@ -213,31 +305,28 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
                 const int sn = (j + PD) & (ISLOTS - 1), ss = (j + PD) & (SSLOTS - 1);
 #pragma unroll
                 for (int r = 0; r < SR; ++r) {
-                    cp_async4(s_idx + (si * SR + r) * 256, cp + ji * SE + r * G);
-                    if (HAS_VAL) cp_async4(s_val + (si * SR + r) * 256, vp + ji * SE + r * G);
-                    const int rawn = s_idx[(sn * SR + r) * 256];
+                    cp_async4(s_idx + (si * SR + r) * NT, cp + ji * SE + r * G);
+                    if (HAS_VAL) cp_async4(s_val + (si * SR + r) * NT, vp + ji * SE + r * G);
+                    const int rawn = s_idx[(sn * SR + r) * NT];
                     unsigned e = (__ballot_sync(FULL, rawn < 0) >> gshift) & gbits;
                     if (j + PD >= n_slabs) e = 0;      // past the chunk: the replayed slab is never processed
-                    cp_async4(s_seg + (ss * SR + r) * 256, seg_row + s + __popc(e & lt));
+                    if (!PPNP_SPMM_SEGPRED || rawn < 0) cp_async4(s_seg + (ss * SR + r) * NT, seg_row + s + __popc(e & lt));
                     s += __popc(e);
                 }
                 cp_async_commit();
             }
             // the slab to process
-            int raw0[SR], segv0[SR];
-            float w0[SR];
-            unsigned ends0[SR];
-            unsigned any_end = 0;
             {
                 const int s0 = j & (ISLOTS - 1), q0 = j & (SSLOTS - 1);
 #pragma unroll
                 for (int r = 0; r < SR; ++r) {
-                    raw0[r] = s_idx[(s0 * SR + r) * 256];
-                    segv0[r] = s_seg[(q0 * SR + r) * 256];
-                    if (HAS_VAL) w0[r] = s_val[(s0 * SR + r) * 256];
+                    raw0[r] = s_idx[(s0 * SR + r) * NT];
+                    segv0[r] = s_seg[(q0 * SR + r) * NT];
+                    if (HAS_VAL) w0[r] = s_val[(s0 * SR + r) * NT];
                     ends0[r] = (__ballot_sync(FULL, raw0[r] < 0) >> gshift) & gbits;
                     any_end |= ends0[r];
                 }
+            }
             }
 
             if (!__any_sync(FULL, any_end != 0)) {
@@ -317,15 +406,15 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
     }
 }
 
-template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE, bool PUSH>
-__global__ void __launch_bounds__(256, (G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOCKS : PPNP_SPMM_MINBLOCKS_WIDE)
+template <int VEC, int G, bool HAS_VAL, int U, bool FULL_TILE, bool PUSH, int NT = 256, bool IDX16 = false>
+__global__ void __launch_bounds__(NT, (NT == 1024) ? 1 : ((G >= 16 && !HAS_VAL) ? PPNP_SPMM_MINBLOCKS : PPNP_SPMM_MINBLOCKS_WIDE))
 spmm_stream_kernel(const int32_t* __restrict__ cols, const float* __restrict__ vals,
                    const int32_t* __restrict__ seg_row, const int32_t* __restrict__ chunk_seg,
                    int64_t n_chunks, int chunk_edges, const float* Zin, const float* T, float* Zout,
                    float* partial, int ld, int F, float alpha, int epi, const float* __restrict__ row_deg,
                    const __grid_constant__ PushArgs pa) {
-    spmm_stream_body<VEC, G, HAS_VAL, U, FULL_TILE, false, PUSH>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges, Zin, T,
-                                                           Zout, partial, ld, F, alpha, epi, row_deg, &pa);
+    spmm_stream_body<VEC, G, HAS_VAL, U, FULL_TILE, false, PUSH, NT, IDX16>(cols, vals, seg_row, chunk_seg, n_chunks, chunk_edges,
+                                                                      Zin, T, Zout, partial, ld, F, alpha, epi, row_deg, &pa);
 }
 
 // Rows split over several segments: add the partial sums in slot order, then the epilogue.
@@ -451,8 +540,58 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
                                         p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi, p->row_deg, pa); \
     } while (0)
 #define PPNP_LAUNCH(HV_, FT_) do { if (pa.ptr != nullptr) PPNP_LAUNCH2(HV_, FT_, true); else PPNP_LAUNCH2(HV_, FT_, false); } while (0)
-    if (use_vals) { if (full_tile) PPNP_LAUNCH(true, true); else PPNP_LAUNCH(true, false); }
-    else          { if (full_tile) PPNP_LAUNCH(false, true); else PPNP_LAUNCH(false, false); }
+    // plan-selected variants (include/ppnp_b200.h PPNP_PLAN_*): 1024-thread CTAs (one per SM, all its warps on
+    // consecutive chunks) and/or 16-byte staging of a lane-transposed stream.  Built for the two headline
+    // widths only (F = 64: G = 16, F = 16: G = 4), whole feature tiles, no halo push.
+    const int lane_group = PPNP_PLAN_LANE_GROUP(p->flags);
+    const bool wide = (p->flags & PPNP_PLAN_WIDE_CTA) != 0;
+    if (lane_group != 0 && lane_group != G) {
+        set_error("plan is lane-transposed for groups of %d lanes, this feature width uses %d", lane_group, G);
+        return PPNP_EINVAL;
+    }
+    constexpr bool HAS_VARIANTS = (VEC == 4) && (G == 4 || G == 16);
+    bool launched = false;
+    if constexpr (HAS_VARIANTS) {
+        if ((wide || lane_group != 0) && full_tile && pa.ptr == nullptr) {
+#define PPNP_LAUNCH3(HV_, NT_, I16_)                                                                               \
+    do {                                                                                                           \
+        auto k = spmm_stream_kernel<VEC, G, HV_, U, true, false, NT_, I16_>;                                       \
+        static thread_local int occ = 0;                                                                           \
+        const int smem_bytes = (I16_ ? Stage16Cfg<G>::words_per_thread(HV_) : StageCfg<G>::words_per_thread(HV_)) * NT_ * 4; \
+        if (!occ) {                                                                                                \
+            occ = blocks_per_sm(k, NT_, smem_bytes);                                                               \
+            /* leave everything the staging does not need to the L1: the carved blocks live there */               \
+            const int pct = (int)(((int64_t)(smem_bytes + 1024) * occ * 100 + 228 * 1024 - 1) / (228 * 1024));     \
+            cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);        \
+        }                                                                                                          \
+        const int64_t gpb = (NT_ / 32) * GPW;                                                                      \
+        const int64_t need3 = (p->n_chunks + gpb - 1) / gpb;                                                       \
+        const int64_t cap = (int64_t)sm_count() * occ;                                                             \
+        dim3 grid((unsigned)(need3 < cap ? need3 : cap), (unsigned)tiles);                                         \
+        k<<<grid, NT_, smem_bytes, stream>>>(p->cols, HV_ ? p->vals : nullptr, p->seg_row, p->chunk_seg, p->n_chunks,  \
+                                       p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi, p->row_deg, pa); \
+    } while (0)
+            if (use_vals) {
+                if (wide && lane_group) PPNP_LAUNCH3(true, 1024, true);
+                else if (wide) PPNP_LAUNCH3(true, 1024, false);
+                else PPNP_LAUNCH3(true, 256, true);
+            } else {
+                if (wide && lane_group) PPNP_LAUNCH3(false, 1024, true);
+                else if (wide) PPNP_LAUNCH3(false, 1024, false);
+                else PPNP_LAUNCH3(false, 256, true);
+            }
+#undef PPNP_LAUNCH3
+            launched = true;
+        }
+    }
+    if (!launched && lane_group != 0) {
+        set_error("lane-transposed plans run only with F = 16 or 64 (whole tiles, 16-byte aligned) and without a halo push");
+        return PPNP_ENOTSUP;
+    }
+    if (!launched) {
+        if (use_vals) { if (full_tile) PPNP_LAUNCH(true, true); else PPNP_LAUNCH(true, false); }
+        else          { if (full_tile) PPNP_LAUNCH(false, true); else PPNP_LAUNCH(false, false); }
+    }
 #undef PPNP_LAUNCH
 #undef PPNP_LAUNCH2
     PPNP_CHECK_LAUNCH("spmm_stream_kernel");
@@ -569,6 +708,11 @@ int validate_plan(const ppnp_plan_t* p) {
     PPNP_REQUIRE(p->cols && p->seg_row && p->chunk_seg, "plan arrays missing");
     PPNP_REQUIRE(aligned16(p->cols) && (p->vals == nullptr || aligned16(p->vals)), "plan arrays must be 16-byte aligned");
     PPNP_REQUIRE(p->n_fix == 0 || (p->fix_ptr && p->fix_row && p->fix_deg), "fix arrays missing");
+    PPNP_REQUIRE((p->flags & ~(PPNP_PLAN_WIDE_CTA | 0xff00)) == 0, "unknown plan flags");
+    {
+        const int lgp = PPNP_PLAN_LANE_GROUP(p->flags);
+        PPNP_REQUIRE(lgp == 0 || lgp == 4 || lgp == 8 || lgp == 16 || lgp == 32, "lane group must be 4, 8, 16 or 32");
+    }
     return PPNP_OK;
 }
 
@@ -610,7 +754,7 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
     cudaStream_t stream = as_stream(stream_);
     // small graphs: all K steps in one cooperative launch (grid barriers instead of 2K launches)
     if (K >= 2 && plan->vals != nullptr && plan->row_deg == nullptr && plan->n_chunks <= PPNP_PERSISTENT_MAX_CHUNKS &&
-        persistent_enabled()) {
+        PPNP_PLAN_LANE_GROUP(plan->flags) == 0 && persistent_enabled()) {
         return dispatch_persistent(plan, H, Z, scratch, partial, ld, F, K, alpha, stream);
     }
     const float* src = H;
@@ -667,6 +811,7 @@ int ppnp_appnp_propagate_persistent(const ppnp_plan_t* plan, const float* H, flo
     PPNP_REQUIRE(K >= 1, "K >= 1");
     PPNP_REQUIRE(plan->vals != nullptr, "the persistent kernel uses the stored values");
     PPNP_REQUIRE(plan->row_deg == nullptr, "partial-row streams are not supported here");
+    PPNP_REQUIRE(PPNP_PLAN_LANE_GROUP(plan->flags) == 0, "lane-transposed streams are not supported here");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     return dispatch_persistent(plan, H, Z, scratch, partial, ld, F, K, alpha, as_stream(stream_));
 }

@@ -9,7 +9,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .plan import StreamPlan, build_stream_plan, degree_order
+from .plan import StreamPlan, build_carved_plan, build_stream_plan, degree_order, lane_group_for, lane_transpose
 
 MODE = {"sym": _lib.MODE_SYM, "rw": _lib.MODE_RW}
 
@@ -73,22 +73,42 @@ def csr_normalize(indptr, indices, data=None, mode="sym", want_val64=False, want
 class PropagationGraph:
     """Normalised adjacency + edge-stream plan, ready for ``appnp_propagate``."""
 
-    def __init__(self, ahat: NormalizedCSR, chunk_edges=256, order="natural", keep_vals=True):
+    def __init__(self, ahat: NormalizedCSR, chunk_edges=256, order="natural", keep_vals=True, idx16=False, carve=None):
+        """order: "natural" | "degree" | a permutation tensor (row-major streams, plan.build_stream_plan) or
+        "carve" (hot column blocks first, plan.build_carved_plan; ``carve`` = its keyword arguments).
+        idx16: stage the index stream with 16-byte copies from a lane-transposed copy of the stream
+        (feature widths 16 and 64; other widths keep the linear stream)."""
         self.ahat = ahat
         self.mode = ahat.mode
-        if order == "natural":
-            ord_t = None
-        elif order == "degree":
-            ord_t = degree_order(ahat.indptr)
-        elif torch.is_tensor(order):
-            ord_t = order
-        else:
-            raise ValueError(f"unknown order {order!r}")
         vals = ahat.val32 if keep_vals else None
-        self.plan: StreamPlan = build_stream_plan(ahat.indptr, ahat.indices, vals, chunk_edges, ord_t)
+        if isinstance(order, str) and order == "carve":
+            self.plan: StreamPlan = build_carved_plan(ahat.indptr, ahat.indices, vals, chunk_edges, **(carve or {}))
+        else:
+            if carve is not None:
+                raise ValueError("carve parameters need order='carve'")
+            if isinstance(order, str) and order == "natural":
+                ord_t = None
+            elif isinstance(order, str) and order == "degree":
+                ord_t = degree_order(ahat.indptr)
+            elif torch.is_tensor(order):
+                ord_t = order
+            else:
+                raise ValueError(f"unknown order {order!r}")
+            self.plan = build_stream_plan(ahat.indptr, ahat.indices, vals, chunk_edges, ord_t)
         self.n = ahat.n
         self.nnz = ahat.nnz
+        self.idx16 = bool(idx16)
+        self._plans16 = {}
         self._partial = {}
+
+    def plan_for(self, F):
+        """The stream a propagation over F features reads (lane-transposed copy when idx16 applies)."""
+        if not self.idx16 or F not in (16, 64):
+            return self.plan
+        G = lane_group_for(F)
+        if G not in self._plans16:
+            self._plans16[G] = lane_transpose(self.plan, G)
+        return self._plans16[G]
 
     @classmethod
     def from_adjacency(cls, indptr, indices, data=None, mode="sym", **kw):
@@ -115,7 +135,7 @@ def spmm_step(graph: PropagationGraph, Zin, T, alpha, epi=_lib.EPI_PLAIN, use_va
         out = torch.empty_like(Zin)
     partial = graph.partial_buffer(F)
     with torch.cuda.device(Zin.device):
-        rc = lib.ppnp_spmm_step(graph.plan.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), _lib.ptr(partial),
+        rc = lib.ppnp_spmm_step(graph.plan_for(F).struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), _lib.ptr(partial),
                                 F, F, float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
     _lib.check(rc, "ppnp_spmm_step")
     return out
@@ -141,7 +161,7 @@ def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False,
     scratch = scratch if scratch is not None else torch.empty_like(H)
     partial = graph.partial_buffer(F)
     with torch.cuda.device(H.device):
-        rc = lib.ppnp_appnp_propagate(graph.plan.struct(), _lib.ptr(H), _lib.ptr(Z), _lib.ptr(scratch),
+        rc = lib.ppnp_appnp_propagate(graph.plan_for(F).struct(), _lib.ptr(H), _lib.ptr(Z), _lib.ptr(scratch),
                                       _lib.ptr(partial), F, F, int(K), float(alpha), MODE[graph.mode],
                                       int(bool(use_vals)), _lib.current_stream())
     _lib.check(rc, "ppnp_appnp_propagate")

@@ -19,6 +19,8 @@ import torch
 from . import _lib
 
 FLAG_I32 = -(1 << 31)          # PPNP_FLAG as a signed int32
+PLAN_WIDE_CTA = 1              # ppnp_plan_t.flags bit 0 (include/ppnp_b200.h)
+PLAN_LANE_GROUP_SHIFT = 8      # ppnp_plan_t.flags bits 8..15: lane group of a lane-transposed stream
 
 
 @dataclass
@@ -38,6 +40,9 @@ class StreamPlan:
     order: Optional[torch.Tensor] = None   # processing order of the rows (None = natural)
     n_segs_real: int = 0
     row_deg: Optional[torch.Tensor] = None  # fp32 [n]: full row degrees for partial-row streams
+    wide_cta: bool = False      # PPNP_PLAN_WIDE_CTA: one 1024-thread CTA per SM walks consecutive chunks
+    lane_group: int = 0         # > 0: cols/vals are stored lane-transposed for groups of this many lanes
+    carve: Optional[dict] = None  # statistics of build_carved_plan (None for row-major streams)
     _struct: object = field(default=None, repr=False)
 
     @property
@@ -58,7 +63,8 @@ class StreamPlan:
             s = _lib.PlanStruct()
             s.n, s.n_edges, s.n_chunks = self.n, self.n_chunks * self.chunk_edges, self.n_chunks
             s.n_segs, s.n_fix, s.n_slots = self.n_segs, self.n_fix, self.n_slots
-            s.chunk_edges, s.reserved = self.chunk_edges, 0
+            s.chunk_edges = self.chunk_edges
+            s.flags = (PLAN_WIDE_CTA if self.wide_cta else 0) | (self.lane_group << PLAN_LANE_GROUP_SHIFT)
             s.cols = self.cols.data_ptr()
             s.vals = self.vals.data_ptr() if self.vals is not None else None
             s.seg_row = self.seg_row.data_ptr()
@@ -79,7 +85,8 @@ class StreamPlan:
         mv = lambda t: None if t is None else t.to(device)
         return StreamPlan(self.n, self.nnz, self.chunk_edges, self.n_chunks, mv(self.cols), mv(self.vals),
                           mv(self.seg_row), mv(self.chunk_seg), mv(self.fix_ptr), mv(self.fix_row),
-                          mv(self.fix_deg), self.n_slots, mv(self.order), self.n_segs_real, mv(self.row_deg))
+                          mv(self.fix_deg), self.n_slots, mv(self.order), self.n_segs_real, mv(self.row_deg),
+                          self.wide_cta, self.lane_group, self.carve)
 
 
 def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None, subset=False, row_deg=None):
@@ -188,3 +195,163 @@ def degree_order(indptr):
     ip = indptr.to(torch.int64)
     deg = ip[1:] - ip[:-1]
     return torch.sort(deg, descending=True, stable=True).indices
+
+
+def _plan_from_runs(n, run_row, run_len, stream_cols, stream_vals, chunk_edges, full_deg, rank, order=None):
+    """Generic stream builder: ``run_row[i]`` / ``run_len[i]`` list, in stream order, runs of edges that
+    belong to one row (a row may own several runs anywhere in the stream).  Runs are cut at chunk
+    boundaries; a row whose edges end up in more than one segment gets one partial slot per segment
+    (slots of a row are contiguous, rows in ``rank`` order) and is finished by the fix-up kernel."""
+    dev = stream_cols.device
+    W = chunk_edges
+    nnz = int(stream_cols.numel())
+    L = run_len.to(torch.int64)
+    a = torch.cumsum(L, 0) - L
+    b = a + L
+    ca = torch.div(a, W, rounding_mode="floor")
+    cb = torch.div(b - 1, W, rounding_mode="floor")
+    pieces = cb - ca + 1
+    n_runs = int(L.numel())
+    n_segs = int(pieces.sum().item())
+    owner = torch.repeat_interleave(torch.arange(n_runs, device=dev, dtype=torch.int64), pieces)
+    first = torch.cumsum(pieces, 0) - pieces
+    q = torch.arange(n_segs, device=dev, dtype=torch.int64) - first[owner]
+    cq = ca[owner] + q
+    seg_start = torch.maximum(a[owner], cq * W)
+    seg_end = torch.minimum(b[owner], (cq + 1) * W) - 1
+    seg_owner_row = run_row.to(torch.int64)[owner]
+    del first, q, cq, owner
+
+    per_row = torch.bincount(seg_owner_row, minlength=n)
+    if bool((per_row == 0).any()):
+        raise ValueError("every row needs at least one edge in the stream")
+    split_row = per_row > 1
+    # fix rows in rank order (heaviest first); slots of a row are contiguous
+    fix_rows = torch.nonzero(split_row).flatten()
+    fix_rows = fix_rows[torch.argsort(rank[fix_rows], stable=True)]
+    n_fix = int(fix_rows.numel())
+    fp = torch.zeros(n_fix + 1, dtype=torch.int64, device=dev)
+    if n_fix:
+        fp[1:] = torch.cumsum(per_row[fix_rows], 0)
+    n_slots = int(fp[-1].item())
+    slot_base = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    slot_base[fix_rows] = fp[:-1]
+    # index of every segment among the segments of its row, in stream order
+    by_row = torch.argsort(seg_owner_row, stable=True)
+    row_first = torch.cumsum(per_row, 0) - per_row
+    k_in_row = torch.empty(n_segs, dtype=torch.int64, device=dev)
+    k_in_row[by_row] = torch.arange(n_segs, device=dev, dtype=torch.int64) - row_first[seg_owner_row[by_row]]
+    seg_partial = split_row[seg_owner_row]
+    slot = slot_base[seg_owner_row] + k_in_row
+    seg_row = torch.where(seg_partial, slot + FLAG_I32, seg_owner_row).to(torch.int32)
+    seg_row = torch.cat([seg_row, torch.zeros(64, dtype=torch.int32, device=dev)])
+
+    n_chunks = (nnz + W - 1) // W
+    n_chunks = ((n_chunks + 31) // 32) * 32
+    total = n_chunks * W
+    cols = torch.zeros(total, dtype=torch.int32, device=dev)
+    cols[:nnz] = stream_cols.to(torch.int32)
+    cols[seg_end] |= FLAG_I32
+    svals = None
+    if stream_vals is not None:
+        svals = torch.zeros(total, dtype=torch.float32, device=dev)
+        svals[:nnz] = stream_vals.to(torch.float32)
+    chunk_starts = torch.arange(n_chunks, device=dev, dtype=torch.int64) * W
+    chunk_seg = torch.searchsorted(seg_start.contiguous(), chunk_starts, right=False).to(torch.int32)
+    return StreamPlan(n=n, nnz=nnz, chunk_edges=W, n_chunks=n_chunks, cols=cols, vals=svals, seg_row=seg_row,
+                      chunk_seg=chunk_seg, fix_ptr=fp.to(torch.int32), fix_row=fix_rows.to(torch.int32),
+                      fix_deg=full_deg[fix_rows].to(torch.float32), n_slots=n_slots, order=order,
+                      n_segs_real=n_segs)
+
+
+def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=512, n_blocks=64, min_piece=4,
+                      wide_cta=True):
+    """Edge stream with the hot column blocks carved out ("carved stream").
+
+    Columns are ranked by degree; block b holds the columns of rank [b * block_cols, (b+1) * block_cols)
+    for b < n_blocks -- ``block_cols`` rows of the feature matrix are meant to fit one SM's L1.  The
+    edges of a row that fall into one block form a *piece*; pieces of at least ``min_piece`` edges are
+    taken out of their row and streamed block by block (rows in degree order inside a block), so
+    that an SM walking consecutive chunks keeps gathering the same ``block_cols`` rows.  What is left
+    of every row follows in degree order, exactly as in ``build_stream_plan(order=degree_order)``.
+    Every carved row becomes a split row (partial sums + fix-up), results are order-deterministic.
+    Column ids are not relabelled.
+    """
+    if chunk_edges % 128 != 0 or chunk_edges <= 0:
+        raise ValueError("chunk_edges must be a positive multiple of 128")
+    if block_cols <= 0 or n_blocks < 0 or min_piece < 1:
+        raise ValueError("block_cols > 0, n_blocks >= 0, min_piece >= 1")
+    dev = indices.device
+    n = int(indptr.numel()) - 1
+    ip = indptr.to(torch.int64)
+    nnz = int(ip[-1].item())
+    if nnz != int(indices.numel()):
+        raise ValueError("indptr[-1] != len(indices)")
+    deg = ip[1:] - ip[:-1]
+    if bool((deg <= 0).any()):
+        raise ValueError("every streamed row needs at least one edge (A_hat rows hold their self loop)")
+    order = degree_order(indptr)
+    rank = torch.empty(n, dtype=torch.int64, device=dev)
+    rank[order] = torch.arange(n, device=dev, dtype=torch.int64)
+    NB = int(min(n_blocks, (n + block_cols - 1) // block_cols))
+    row_of = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), deg)
+    blk = torch.div(rank[indices.to(torch.int64)], block_cols, rounding_mode="floor").clamp_(max=NB)
+    # edges per (row, block): CSR order is row-major, so a stable sort by block inside the row groups them
+    key = row_of * (NB + 1) + blk
+    skey, perm = torch.sort(key, stable=True)
+    _, inv, cnt = torch.unique_consecutive(skey, return_inverse=True, return_counts=True)
+    keep = (cnt[inv] >= min_piece) & ((skey % (NB + 1)) < NB)
+    fblk = torch.full((nnz,), NB, dtype=torch.int64, device=dev)
+    fblk[perm] = torch.where(keep, skey % (NB + 1), torch.full_like(skey, NB))
+    carved_edges = int(keep.sum().item())
+    del key, skey, inv, cnt, keep, blk
+    # stream order: (block, rank of the row), columns ascending inside a run (stable sort of CSR order)
+    key2 = fblk * n + rank[row_of]
+    skey2, perm2 = torch.sort(key2, stable=True)
+    run_key, run_len = torch.unique_consecutive(skey2, return_counts=True)
+    run_row = order[run_key % n]
+    stream_cols = indices[perm2]
+    stream_vals = None if vals is None else vals[perm2]
+    n_carved_runs = int((run_key < NB * n).sum().item())
+    del key2, skey2, perm2, fblk, row_of
+    plan = _plan_from_runs(n, run_row, run_len, stream_cols, stream_vals, chunk_edges, deg, rank, order)
+    plan.wide_cta = bool(wide_cta)
+    plan.carve = {"block_cols": block_cols, "n_blocks": NB, "min_piece": min_piece, "carved_edges": carved_edges,
+                  "carved_pieces": n_carved_runs, "n_slots": plan.n_slots, "n_fix": plan.n_fix}
+    return plan
+
+
+def lane_group_for(F):
+    """Lane group the propagation kernel uses for feature width F (csrc/appnp_spmm.cu dispatch_step)."""
+    g = 1
+    w = F // 4 if F % 4 == 0 else F
+    while g < w:
+        g <<= 1
+    return min(g, 32)
+
+
+def lane_transpose(plan: StreamPlan, G):
+    """Copy of ``plan`` whose cols / vals are stored lane-transposed for lane groups of G lanes
+    (include/ppnp_b200.h PPNP_PLAN_LANE_GROUP): each lane's 4 index words of 4/SR consecutive slabs
+    are contiguous, so the kernel stages them with one 16-byte cp.async per lane."""
+    if G not in (4, 8, 16, 32):
+        raise ValueError("lane-transposed streams exist for lane groups of 4, 8, 16 or 32")
+    if plan.lane_group:
+        raise ValueError("plan is already lane-transposed")
+    W = plan.chunk_edges
+    SR = max(1, 16 // G)
+    SE = SR * G
+    CPS = 4 // SR
+    if (W // SE) % CPS != 0:
+        raise ValueError("chunk_edges does not hold whole staging quads for this lane group")
+    dev = plan.cols.device
+    p = torch.arange(W, device=dev, dtype=torch.int64)
+    j, r, l = p // SE, (p % SE) // G, p % G
+    stored = (j // CPS) * (CPS * SE) + l * 4 + (j % CPS) * SR + r
+    src = torch.empty(W, dtype=torch.int64, device=dev)
+    src[stored] = p                                   # stored position -> logical position
+    cols = plan.cols.view(plan.n_chunks, W)[:, src].contiguous().view(-1)
+    vals = None if plan.vals is None else plan.vals.view(plan.n_chunks, W)[:, src].contiguous().view(-1)
+    return StreamPlan(plan.n, plan.nnz, W, plan.n_chunks, cols, vals, plan.seg_row, plan.chunk_seg, plan.fix_ptr,
+                      plan.fix_row, plan.fix_deg, plan.n_slots, plan.order, plan.n_segs_real, plan.row_deg,
+                      plan.wide_cta, G, plan.carve)

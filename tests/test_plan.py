@@ -103,3 +103,99 @@ def test_rejects_rows_without_self_loop():
     idx = torch.tensor([0], dtype=torch.int32)
     with pytest.raises(ValueError):
         build_stream_plan(ip, idx, None, 128, None)
+
+
+# ------------------------------------------------------------------ carved streams / lane-transposed layout
+from ppnp_b200.plan import build_carved_plan, lane_transpose, lane_group_for  # noqa: E402
+
+
+@pytest.mark.parametrize("name,block_cols,n_blocks,min_piece",
+                         [("citeseer", 16, 8, 2), ("citeseer", 64, 4, 3), ("cora_ml", 512, 64, 4)])
+def test_carved_stream_walk_matches_oracle(name, block_cols, n_blocks, min_piece):
+    ah, ip, idx, val = ahat_tensors(name)
+    g = load_golden(name)
+    H = g["H"].astype(np.float64)
+    p = build_carved_plan(ip, idx, val, 128, block_cols, n_blocks, min_piece)
+    assert p.wide_cta and p.carve["carved_edges"] > 0
+    ref = oracle.appnp(ah, H, 0.1, 1)
+    assert relerr(walk_stream(p, H, H, 0.1, epi=0, use_vals=True), ref) < 1e-7
+    # value-free Y-space steps use the row degree: fix_deg for split rows, segment length otherwise
+    K, alpha = 3, 0.1
+    Z = walk_stream(p, H, H, alpha, epi=1, use_vals=True)
+    Z = walk_stream(p, Z, H, alpha, epi=2, use_vals=False)
+    Z = walk_stream(p, Z, H, alpha, epi=3, use_vals=False)
+    assert relerr(Z, oracle.appnp(ah, H, alpha, K)) < 1e-7
+
+
+def test_carved_stream_structure():
+    ah, ip, idx, val = ahat_tensors("cora_ml")
+    W, BC, NB, T = 128, 32, 6, 3
+    p = build_carved_plan(ip, idx, val, W, BC, NB, T)
+    cols = p.cols.numpy()
+    ends = np.nonzero(cols < 0)[0]
+    starts = np.concatenate([[0], ends[:-1] + 1])
+    assert len(ends) == p.n_segs and (starts // W == ends // W).all()
+    assert np.array_equal(p.chunk_seg.numpy(), np.searchsorted(starts, np.arange(p.n_chunks) * W, side="left"))
+    # every edge of A_hat appears exactly once
+    deg = np.diff(ah.indptr)
+    sr = p.seg_row.numpy()[:p.n_segs]
+    fp, fr = p.fix_ptr.numpy(), p.fix_row.numpy()
+    slot_row = np.repeat(fr, np.diff(fp))
+    seg_rows = np.where(sr < 0, slot_row[np.where(sr < 0, sr & 0x7FFFFFFF, 0)], sr)
+    rows_of_edges = np.repeat(seg_rows, ends - starts + 1)
+    c = cols[:ah.nnz] & 0x7FFFFFFF
+    got = np.lexsort((c, rows_of_edges))
+    want_rows = np.repeat(np.arange(p.n), deg)
+    assert np.array_equal(rows_of_edges[got], want_rows) and np.array_equal(c[got], ah.indices)
+    # slots: each used once, contiguous per fix row; fix rows have >= 2 segments, others exactly one final
+    slots = np.sort(sr[sr < 0] & 0x7FFFFFFF)
+    assert np.array_equal(slots, np.arange(p.n_slots)) and (np.diff(fp) >= 2).all()
+    finals = sr[sr >= 0]
+    assert len(finals) + p.n_fix == p.n and len(set(finals.tolist()) & set(fr.tolist())) == 0
+    assert (p.fix_deg.numpy() == deg[fr]).all()
+    # the carved part comes first, block by block: column ranks of carved pieces stay inside their block
+    order = degree_order(ip).numpy()
+    rank = np.empty(p.n, dtype=np.int64)
+    rank[order] = np.arange(p.n)
+    n_carved = p.carve["carved_edges"]
+    blk = rank[c[:n_carved]] // BC
+    assert (np.diff(blk) >= 0).all() and blk.max() < NB
+    # pieces honour min_piece before chunk cuts: count edges per (row, block) in the carved part
+    key = rows_of_edges[:n_carved] * NB + blk
+    _, cnt = np.unique(key, return_counts=True)
+    assert cnt.min() >= T
+
+
+def test_carve_nothing_equals_degree_order_stream():
+    ah, ip, idx, val = ahat_tensors("citeseer")
+    a = build_carved_plan(ip, idx, val, 128, 64, 0, 4)
+    b = build_stream_plan(ip, idx, val, 128, degree_order(ip))
+    assert torch.equal(a.cols, b.cols) and torch.equal(a.vals, b.vals) and torch.equal(a.chunk_seg, b.chunk_seg)
+    assert a.n_slots == b.n_slots and a.n_fix == b.n_fix
+
+
+@pytest.mark.parametrize("G", [4, 8, 16, 32])
+def test_lane_transposed_layout_walks_to_the_same_result(G):
+    ah, ip, idx, val = ahat_tensors("citeseer")
+    H = np.random.RandomState(2).randn(ah.shape[0], 3)
+    p = build_stream_plan(ip, idx, val, 128, degree_order(ip))
+    q = lane_transpose(p, G)
+    assert q.lane_group == G and (q.struct().flags >> 8) == G
+    assert not torch.equal(q.cols, p.cols)
+    # the 4 words a lane stages with one 16-byte copy are the words it consumes over 4/SR slabs
+    SR = max(1, 16 // G); SE = SR * G; CPS = 4 // SR
+    c0, q0 = p.cols.numpy()[:128], q.cols.numpy()[:128]
+    for quad in range(128 // (CPS * SE)):
+        for lane in range(G):
+            mine = [c0[(quad * CPS + s) * SE + r * G + lane] for s in range(CPS) for r in range(SR)]
+            base = quad * CPS * SE + lane * 4
+            assert list(q0[base:base + 4]) == mine
+    a = walk_stream(p, H, H, 0.1, 0, True)
+    b = walk_stream(q, H, H, 0.1, 0, True)
+    assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        lane_transpose(q, G)
+
+
+def test_lane_group_for_matches_dispatch():
+    assert [lane_group_for(F) for F in (64, 16, 32, 128, 256, 7, 3, 1, 48)] == [16, 4, 8, 32, 32, 8, 4, 1, 16]

@@ -51,6 +51,16 @@ def walk_stream(plan, Zin, T, alpha, epi, use_vals):
     seg_row = plan.seg_row.cpu().numpy()
     chunk_seg = plan.chunk_seg.cpu().numpy()
     W = plan.chunk_edges
+    if plan.lane_group:   # lane-transposed storage (include/ppnp_b200.h): read logical position p from `stored`
+        G = plan.lane_group
+        SR = max(1, 16 // G)
+        SE, CPS = SR * G, 4 // SR
+        p = np.arange(W)
+        j, r, l = p // SE, (p % SE) // G, p % G
+        stored = (j // CPS) * (CPS * SE) + l * 4 + (j % CPS) * SR + r
+        cols = cols.reshape(-1, W)[:, stored].reshape(-1)
+        if vals is not None:
+            vals = vals.reshape(-1, W)[:, stored].reshape(-1)
     F = Zin.shape[1]
     out = np.full((plan.n, F), np.nan)
     partial = np.full((max(plan.n_slots, 1), F), np.nan)
