@@ -105,6 +105,59 @@ def batch_step(ppr_sparsified, idx_batch, H_full):
 _clib = None
 
 
+def standardize(indptr, indices, data=None, make_unweighted=True, make_undirected=True, no_self_loops=True,
+                select_lcc=True):
+    """ppnp/data/sparsegraph.py:191-222 ``SparseGraph.standardize`` restated on CSR arrays in numpy.
+
+    to_unweighted (:150-154): every stored entry becomes 1.  to_undirected (:127-148): A + A.T with
+    the doubly-present entries (opposing pairs, self loops) counted once -- for unit weights the
+    pattern union with all values 1.  remove_self_loops (:381-395): diagonal entries dropped.
+    largest_connected_components (:355-379): scipy's weakly connected components (numbered by their
+    smallest node), ``np.argsort(sizes)[::-1][:1]`` picks the one to keep, create_subgraph (:300-352)
+    keeps its nodes in ascending order and relabels.  Returns (indptr int64, indices int32, kept node
+    ids int64); the data of the result is all ones.  Only the unit-weight pipeline is restated
+    (``make_unweighted=True``, what main.py:75 runs); stored explicit zeros are not supported.
+    """
+    if not make_unweighted:
+        raise NotImplementedError("only the make_unweighted=True pipeline of main.py:75 is restated")
+    indptr = np.asarray(indptr, dtype=np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    if data is not None and (np.asarray(data) == 0).any():
+        raise ValueError("explicit zeros in the adjacency are not supported")
+    n = len(indptr) - 1
+    r = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    c = indices
+    if make_undirected:
+        r, c = np.concatenate([r, c]), np.concatenate([c, r])
+    if no_self_loops:
+        m = r != c
+        r, c = r[m], c[m]
+    key = np.unique(r * n + c)
+    r, c = key // n, key % n
+    keep = np.arange(n, dtype=np.int64)
+    if select_lcc and n > 0:
+        lab = np.arange(n, dtype=np.int64)          # -> smallest node id of the (weak) component
+        while True:
+            new = lab.copy()
+            m = np.minimum(lab[r], lab[c])
+            np.minimum.at(new, r, m)
+            np.minimum.at(new, c, m)
+            new = new[new]
+            if np.array_equal(new, lab):
+                break
+            lab = new
+        roots, sizes = np.unique(lab, return_counts=True)   # roots ascending == scipy's component numbering
+        best = roots[np.argsort(sizes)[::-1][:1]]             # the literal expression of sparsegraph.py:374
+        keep = np.nonzero(np.isin(lab, best))[0].astype(np.int64)
+        newid = np.full(n, -1, dtype=np.int64)
+        newid[keep] = np.arange(len(keep))
+        sel = newid[r] >= 0
+        r, c = newid[r[sel]], newid[c[sel]]
+    out_indptr = np.zeros(len(keep) + 1, dtype=np.int64)
+    np.cumsum(np.bincount(r, minlength=len(keep)), out=out_indptr[1:])
+    return out_indptr, c.astype(np.int32), keep
+
+
 def clib():
     """Load oracle/_build/libppnp_oracle.so (built by oracle/Makefile or __graft_entry__.build)."""
     global _clib
