@@ -236,6 +236,34 @@ int ppnp_gather_rows(const float* src, int64_t ld_src, const int64_t* idx, int64
 int ppnp_rmat_keys(uint64_t seed, int32_t scale, int64_t n, int64_t e0, int64_t e1,
                    int64_t* out_keys, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (7) Graph standardisation -- the step right before the path.
+ *     replaces ppnp/data/sparsegraph.py:191-222 SparseGraph.standardize for the unit-weight
+ *     pipeline that main.py:75 / batch-main.py:76 run (make_unweighted=True):
+ *       PPNP_STD_UNDIRECTED     to_undirected :127-148   pattern union of A and A^T
+ *       PPNP_STD_NO_SELF_LOOPS  remove_self_loops :381-395
+ *       PPNP_STD_LCC            largest_connected_components :355-379 + create_subgraph :300-352
+ *                               (weak components; ties between largest components: the one whose
+ *                               smallest node id is largest, = np.argsort(sizes)[::-1][0] of a stable sort)
+ * in : CSR pattern of the raw adjacency, indptr int64[n+1], indices int32[nnz] (any order inside a
+ *      row, duplicates allowed; stored weights are never read: every entry counts as 1).
+ * out: canonical CSR of the standardised graph, bit-exact with the reference:
+ *        out_indptr  int64[n+1]   (n_keep + 1 entries used)
+ *        out_indices int32[cap]   cap = 2 * nnz with PPNP_STD_UNDIRECTED, else nnz
+ *        out_keep    int32[n]     original ids of the kept nodes, ascending (n_keep entries used)
+ *        out_counts  int64[3]     DEVICE: {n_keep, nnz_out, status}; status != 0: a column index
+ *                                 was outside [0, n) and the result is invalid.
+ * Everything is stream-ordered; the caller reads out_counts after synchronising.
+ * workspace: ppnp_graph_standardize_workspace_bytes(n, nnz, flags) bytes (~34 B per key + 40 B per node).
+ * ---------------------------------------------------------------------------------------- */
+#define PPNP_STD_UNDIRECTED 1
+#define PPNP_STD_NO_SELF_LOOPS 2
+#define PPNP_STD_LCC 4
+int64_t ppnp_graph_standardize_workspace_bytes(int64_t n, int64_t nnz, int32_t flags);
+int ppnp_graph_standardize(const int64_t* indptr, const int32_t* indices, int64_t n, int64_t nnz, int32_t flags,
+                           int64_t* out_indptr, int32_t* out_indices, int32_t* out_keep, int64_t* out_counts,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("PPNP_B200_LIB") or os.path.join(_HERE, "libppnp_b200.
 MODE_SYM, MODE_RW = 0, 1
 EPI_PLAIN, EPI_Z2Y, EPI_Y, EPI_Y2Z, EPI_RW = 0, 1, 2, 3, 4
 EPI_ACC = 16
+STD_UNDIRECTED, STD_NO_SELF_LOOPS, STD_LCC = 1, 2, 4
 FLAG = 0x80000000
 
 
@@ -55,6 +56,8 @@ SIGNATURES = {
     "ppnp_batch_propagate": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _i32, _p]),
     "ppnp_gather_rows": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _p]),
     "ppnp_rmat_keys": (C.c_int, [_u64, _i32, _i64, _i64, _i64, _p, _p]),
+    "ppnp_graph_standardize_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "ppnp_graph_standardize": (C.c_int, [_p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _i64, _p]),
 }
 
 _lib = None

@@ -458,3 +458,46 @@ def gather_rows(src, idx, out):
                                   out.stride(0), _lib.current_stream())
     _lib.check(rc, "ppnp_gather_rows")
     return out
+
+
+# ------------------------------------------------------------------------------ graph standardisation
+def graph_standardize(indptr, indices, make_unweighted=True, make_undirected=True, no_self_loops=True, select_lcc=True):
+    """ppnp/data/sparsegraph.py:191-222 ``SparseGraph.standardize`` on the GPU (csrc/standardize.cu).
+
+    indptr / indices: CSR pattern of the raw adjacency as CUDA tensors (weights are never read: the
+    pipeline of main.py:75 sets them to 1 first).  Returns ``(indptr, indices, keep)``: the canonical
+    CSR of the standardised graph (int32 when it fits, the contract of ``csr_normalize``) and the
+    original ids of the kept nodes (int64, ascending) for subsetting attributes and labels.
+    """
+    if not make_unweighted:
+        raise NotImplementedError("only the make_unweighted=True pipeline (main.py:75) exists on the GPU")
+    lib = _lib.load()
+    _require_cuda(indptr, indices)
+    dev = indices.device
+    indptr = indptr.to(torch.int64).contiguous()
+    indices = indices.to(torch.int32).contiguous()
+    n = indptr.numel() - 1
+    nnz = indices.numel()
+    if n <= 0:
+        raise ValueError("empty graph")
+    flags = ((_lib.STD_UNDIRECTED if make_undirected else 0) | (_lib.STD_NO_SELF_LOOPS if no_self_loops else 0) |
+             (_lib.STD_LCC if select_lcc else 0))
+    cap = max(1, 2 * nnz if make_undirected else nnz)
+    out_indptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    out_indices = torch.empty(cap, dtype=torch.int32, device=dev)
+    out_keep = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.empty(3, dtype=torch.int64, device=dev)
+    ws_bytes = lib.ppnp_graph_standardize_workspace_bytes(n, nnz, flags)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ppnp_graph_standardize(_lib.ptr(indptr), _lib.ptr(indices), n, nnz, flags, _lib.ptr(out_indptr),
+                                        _lib.ptr(out_indices), _lib.ptr(out_keep), _lib.ptr(counts), _lib.ptr(ws), ws_bytes,
+                                        _lib.current_stream())
+    _lib.check(rc, "ppnp_graph_standardize")
+    n_keep, nnz_out, status = (int(x) for x in counts.tolist())
+    if status != 0:
+        raise ValueError("graph_standardize: a column index lies outside [0, n)")
+    ip = out_indptr[:n_keep + 1]
+    if nnz_out < (1 << 31):
+        ip = ip.to(torch.int32)
+    return ip, out_indices[:nnz_out], out_keep[:n_keep].to(torch.int64)

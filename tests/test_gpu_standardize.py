@@ -1,0 +1,93 @@
+"""Graph standardisation on the GPU (csrc/standardize.cu) against the reference's own outputs
+(tests/golden/standardize_cases.npz) and the numpy restatement.  Needs a GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from util import GOLDEN, oracle
+
+pytestmark = pytest.mark.gpu
+CASES = np.load(os.path.join(GOLDEN, "standardize_cases.npz"))
+NAMES = [str(x) for x in CASES["names"]]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def run(ip, idx, **flags):
+    import ppnp_b200 as P
+    a, b, c = P.graph_standardize(torch.from_numpy(np.asarray(ip)).to(dev()), torch.from_numpy(np.asarray(idx)).to(dev()), **flags)
+    return a.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_standardize_bit_exact_with_reference(name):
+    f = CASES[f"{name}.flags"]
+    flags = dict(make_unweighted=bool(f[0]), make_undirected=bool(f[1]), no_self_loops=bool(f[2]), select_lcc=bool(f[3]))
+    ip, idx, keep = run(CASES[f"{name}.in_indptr"], CASES[f"{name}.in_indices"], **flags)
+    assert np.array_equal(ip, CASES[f"{name}.out_indptr"])
+    assert np.array_equal(idx, CASES[f"{name}.out_indices"])
+    assert np.array_equal(keep, CASES[f"{name}.keep"])
+    assert idx.dtype == np.int32 and ip.dtype == np.int32 and keep.dtype == np.int64
+
+
+def test_standardize_feeds_the_hot_path():
+    """raw cora_ml -> standardise -> A_hat on the GPU == the reference's calc_A_hat on its own standardised graph."""
+    import ppnp_b200 as P
+    from util import load_golden
+    ip, idx, keep = P.graph_standardize(torch.from_numpy(CASES["cora_ml.in_indptr"]).to(dev()),
+                                        torch.from_numpy(CASES["cora_ml.in_indices"]).to(dev()))
+    ahat = P.csr_normalize(ip, idx)
+    g = load_golden("cora_ml")
+    assert np.array_equal(ahat.indptr.cpu().numpy(), g["ahat_sym_indptr"])
+    assert np.array_equal(ahat.indices.cpu().numpy(), g["ahat_sym_indices"])
+
+
+@pytest.mark.parametrize("n,raw,scale", [(20000, 60000, 15), (200000, 3000000, 18)])
+def test_standardize_rmat_vs_oracle(n, raw, scale):
+    """Skewed, disconnected R-MAT graphs (39 % isolated nodes at the config-4 recipe): one-directional raw
+    draws with duplicates and loops in, the oracle's restatement of the reference out."""
+    rng = np.random.RandomState(n)
+    sip, sidx = oracle.rmat_graph(n, raw, scale, seed=3)             # symmetric, canonical
+    r = np.repeat(np.arange(n), np.diff(sip)); c = sidx.astype(np.int64)
+    keep_dir = (r < c) | (rng.rand(len(r)) < 0.3)                      # drop most of the reverse edges
+    r, c = r[keep_dir], c[keep_dir]
+    loops = rng.randint(0, n, 500)
+    r = np.concatenate([r, loops, r[:1000]]); c = np.concatenate([c, loops, c[:1000]])   # loops and duplicates
+    order = rng.permutation(len(r))                                    # unsorted inside the rows
+    order = order[np.argsort(r[order], kind="stable")]
+    r, c = r[order], c[order]
+    ip = np.zeros(n + 1, dtype=np.int64); np.cumsum(np.bincount(r, minlength=n), out=ip[1:])
+    want = oracle.standardize(ip, c)
+    got = run(ip, c.astype(np.int32))
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    # properties: symmetric pattern, no loops, idempotent
+    again = run(got[0], got[1])
+    assert np.array_equal(again[0], got[0]) and np.array_equal(again[1], got[1])
+    assert np.array_equal(again[2], np.arange(len(got[2])))
+    rr = np.repeat(np.arange(len(got[2])), np.diff(got[0]))
+    assert (rr != got[1]).all()
+    a = set(zip(rr[:5000].tolist(), got[1][:5000].tolist()))
+    full = set(zip(rr.tolist(), got[1].tolist()))
+    assert all((j, i) in full for (i, j) in a)
+
+
+def test_standardize_edge_cases():
+    # no edges at all: every node is its own component, the last one wins the tie (argsort rule)
+    ip, idx, keep = run(np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int32))
+    assert ip.tolist() == [0, 0] and len(idx) == 0 and keep.tolist() == [4]
+    ip, idx, keep = run(np.zeros(6, dtype=np.int64), np.zeros(0, dtype=np.int32), select_lcc=False)
+    assert ip.tolist() == [0] * 6 and keep.tolist() == [0, 1, 2, 3, 4]
+    # only self loops
+    ip, idx, keep = run(np.arange(4, dtype=np.int64), np.arange(3, dtype=np.int32), select_lcc=False)
+    assert ip.tolist() == [0, 0, 0, 0] and len(idx) == 0
+    ip, idx, keep = run(np.arange(4, dtype=np.int64), np.arange(3, dtype=np.int32), select_lcc=False, no_self_loops=False)
+    assert ip.tolist() == [0, 1, 2, 3] and idx.tolist() == [0, 1, 2]
+    # a column outside [0, n) is reported, not a crash
+    with pytest.raises(ValueError):
+        run(np.array([0, 1, 2], dtype=np.int64), np.array([1, 7], dtype=np.int32))
+    with pytest.raises(NotImplementedError):
+        run(np.array([0, 1, 2], dtype=np.int64), np.array([1, 0], dtype=np.int32), make_unweighted=False)

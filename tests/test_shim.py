@@ -210,3 +210,33 @@ def test_batch_main_call_pattern(shim, monkeypatch, batch_mode):
     with torch.no_grad():
         ev = m(X, torch.arange(100).cuda())
     assert relerr(ev.cpu().numpy(), ppr.numpy()[:100].astype(np.float64) @ Hfull) < 1e-5
+
+
+# ------------------------------------------------------------------ ppnp.data.sparsegraph overlay
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="needs the reference checkout (build container only)")
+def test_sparsegraph_overlay_resolves_like_main_py(monkeypatch):
+    """main.py:27-28 imports with [shim, reference] on sys.path: SparseGraph is the GPU-backed subclass,
+    ppnp.preprocessing and the data files still come from the reference, and there is no CPU fallback."""
+    for k in [k for k in sys.modules if k == "ppnp" or k.startswith("ppnp.")]:
+        monkeypatch.delitem(sys.modules, k)
+    monkeypatch.setattr(sys, "path", [SHIM, REFERENCE] + [p for p in sys.path if p not in (SHIM, REFERENCE)])
+    from ppnp.data.sparsegraph import SparseGraph, create_subgraph, largest_connected_components  # noqa: F401
+    from ppnp.preprocessing import gen_splits, normalize_attributes  # noqa: F401
+    import ppnp.preprocessing as prep
+    import ppnp.data.sparsegraph as sgm
+    assert prep.__file__.startswith(REFERENCE) and sgm.__file__.startswith(SHIM)
+    raw = np.load(os.path.join(REFERENCE, "ppnp", "data", "citeseer.npz"), allow_pickle=True)
+    g = SparseGraph.from_flat_dict(dict(raw))
+    assert type(g) is SparseGraph and type(g).__mro__[1].__module__ == "_ppnp_reference_sparsegraph"
+    assert g.num_nodes() == 3312
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            g.standardize(select_lcc=True)
+    else:
+        g.standardize(select_lcc=True)
+        assert g.num_nodes() == 2110 and g.adj_matrix.nnz == 7336
+    for k in [k for k in sys.modules if k == "ppnp" or k.startswith("ppnp.")]:
+        monkeypatch.delitem(sys.modules, k, raising=False)
