@@ -432,7 +432,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--order", default="degree", choices=["natural", "degree", "carve"])
-    ap.add_argument("--idx16", action="store_true", help="16-byte staging of a lane-transposed index stream")
+    ap.add_argument("--idx16", dest="idx16", action="store_true", default=True,
+                    help="16-byte staging of a lane-transposed index stream (default; bit-identical results)")
+    ap.add_argument("--no-idx16", dest="idx16", action="store_false", help="4-byte staging of the linear index stream")
     ap.add_argument("--carve-block-cols", type=int, default=512, help="--order carve: columns per L1-sized block")
     ap.add_argument("--carve-blocks", type=int, default=64, help="--order carve: number of hot column blocks")
     ap.add_argument("--carve-min-piece", type=int, default=4, help="--order carve: smallest (row, block) piece taken out of its row")
