@@ -40,6 +40,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef PPNP_SPMM_SEGPRED
 #define PPNP_SPMM_SEGPRED 0     // 1: only the lanes that end a segment fetch their segment row (4-byte staging path)
 #endif
+#ifndef PPNP_SPMM_FEWENDS
+#define PPNP_SPMM_FEWENDS 0     // 1: slabs with at most two segment ends per group keep the rolling gather ring (experimental)
+#endif
 #ifndef PPNP_SPMM_U4
 #define PPNP_SPMM_U4 4          // float4 gathers issued back to back per group (VEC == 4)
 #endif
@@ -69,6 +72,15 @@ __device__ __forceinline__ void push_row(const Vec<VEC>& o, int row, int ld, int
         const int code = __ldg(pa->code + i);
         o.store(pa->base[(code >> 28) & (PPNP_MAX_PEERS - 1)] + (int64_t)(code & 0x0fffffff) * ld + f);
     }
+}
+
+// Warp-uniform: no lane group of this warp has more than two segment ends in the slab.
+template <int SR, int G>
+__device__ __forceinline__ bool few_ends(const unsigned (&ends0)[SR]) {
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < SR; ++r) c += __popc(ends0[r]);
+    return __all_sync(FULL, c <= 2);
 }
 
 template <typename V, bool COHERENT>
@@ -351,6 +363,65 @@ spmm_stream_body(const int32_t* __restrict__ cols, const float* __restrict__ val
                 for (int e = 0; e < RING; ++e) {
                     if (HAS_VAL) acc.fma(wv[e], v[e]); else acc.add(v[e]);
                 }
+            } else if (PPNP_SPMM_FEWENDS && G >= 4 && few_ends<SR, G>(ends0)) {
+                // ---- rolling path with segment ends: at most two ends per group in this slab (mid-degree rows,
+                // carved pieces).  The gather ring keeps rolling; an end is one group-uniform branch after its
+                // accumulate.  Only a row that is finished here reads its teleport row, at that point.
+                unsigned m = 0;                    // bit k: edge k of the slab ends a segment (k = r * G + lane)
+#pragma unroll
+                for (int r = 0; r < SR; ++r) m |= ends0[r] << (r * G);
+                const int p1 = __ffs(m) - 1;       // >= 0: this branch is taken only when some group has an end,
+                const unsigned m2 = m & (m - 1);   // but MY group may have none (p1 = -1)
+                const int p2 = __ffs(m2) - 1;
+                int sv1 = 0, sv2 = 0;
+                {
+                    const int q1 = p1 < 0 ? 0 : p1, q2 = p2 < 0 ? 0 : p2;
+                    int a1 = segv0[0], a2 = segv0[0];
+#pragma unroll
+                    for (int r = 1; r < SR; ++r) { if (q1 / G == r) a1 = segv0[r]; if (q2 / G == r) a2 = segv0[r]; }
+                    sv1 = __shfl_sync(FULL, a1, q1 % G, G);
+                    sv2 = __shfl_sync(FULL, a2, q2 % G, G);
+                }
+                V v[RING];
+                float wv[RING];
+#pragma unroll
+                for (int e = 0; e < RING; ++e) {
+                    const int col = __shfl_sync(FULL, raw0[e / G], e % G, G) & 0x7fffffff;
+                    if (HAS_VAL) wv[e] = __shfl_sync(FULL, w0[e / G], e % G, G);
+                    v[e].zero();
+                    if (active) v[e] = gather_load<V, COHERENT>(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                }
+#define PPNP_END_CHECK(K_)                                                                                         \
+    if ((K_) == p1 || (K_) == p2) {                                                                                \
+        const int sv = ((K_) == p1) ? sv1 : sv2;                                                                   \
+        const int pos = j * SE + (K_);                                                                             \
+        V t; t.zero();                                                                                             \
+        int pf = -1;                                                                                               \
+        if (sv >= 0) {                                                                                             \
+            if (active) t = V::load_stream(reinterpret_cast<const float*>(tbase + (uint64_t)(unsigned)sv * row_bytes)); \
+            if (PUSH) pf = __ldg(pa->first + sv);                                                                  \
+        }                                                                                                          \
+        {                                                                                                          \
+            const V a2 = acc, t2 = t;                                                                              \
+            emit_segment<VEC, PUSH>(a2, t2, sv, (float)(pos - seg_begin + 1), active, Zout, partial, ld, f, alpha, epi, row_deg, pa, pf); \
+        }                                                                                                          \
+        acc.zero();                                                                                                \
+        seg_begin = pos + 1;                                                                                       \
+    }
+#pragma unroll
+                for (int e = RING; e < SE; ++e) {
+                    if (HAS_VAL) acc.fma(wv[e % RING], v[e % RING]); else acc.add(v[e % RING]);
+                    PPNP_END_CHECK(e - RING)
+                    const int col = __shfl_sync(FULL, raw0[e / G], e % G, G) & 0x7fffffff;
+                    if (HAS_VAL) wv[e % RING] = __shfl_sync(FULL, w0[e / G], e % G, G);
+                    if (active) v[e % RING] = gather_load<V, COHERENT>(reinterpret_cast<const float*>(zbase + (uint64_t)(unsigned)col * row_bytes));
+                }
+#pragma unroll
+                for (int e = 0; e < RING; ++e) {
+                    if (HAS_VAL) acc.fma(wv[(SE - RING + e) % RING], v[(SE - RING + e) % RING]); else acc.add(v[(SE - RING + e) % RING]);
+                    PPNP_END_CHECK(SE - RING + e)
+                }
+#undef PPNP_END_CHECK
             } else {
 #pragma unroll
               for (int r = 0; r < SR; ++r) {

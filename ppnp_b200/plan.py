@@ -264,8 +264,43 @@ def _plan_from_runs(n, run_row, run_len, stream_cols, stream_vals, chunk_edges, 
                       n_segs_real=n_segs)
 
 
+def interleave_chunks(plan: StreamPlan, n_lead_chunks, unit_chunks=64):
+    """Permute the chunks of ``plan`` so that units of ``unit_chunks`` consecutive chunks of its leading part
+    (the first ``n_lead_chunks`` chunks: the carved pieces, served from L1) alternate evenly with units of
+    the rest (the residual rows, whose cold gathers go to DRAM).  Chunks are independent work items --
+    ``chunk_seg[c]`` points at a chunk's segments wherever the chunk sits -- so only cols / vals / chunk_seg
+    move.  Measured reason (profiles/r01_variants.md): streamed back to back, the carved part leaves HBM idle
+    and the residual part then runs at the random-access limit of the DRAM; interleaved, every SM wave
+    mixes both."""
+    nc = plan.n_chunks
+    lead = max(0, min(int(n_lead_chunks), nc))
+    if lead == 0 or lead == nc:
+        return plan
+    dev = plan.cols.device
+    u = int(unit_chunks)
+    n_lead_units = (lead + u - 1) // u
+    n_rest_units = (nc - lead + u - 1) // u
+    # merge the two unit sequences by their fractional position
+    key = torch.cat([(torch.arange(n_lead_units, dtype=torch.float64) + 0.5) / n_lead_units,
+                     (torch.arange(n_rest_units, dtype=torch.float64) + 0.5) / n_rest_units])
+    start = torch.cat([torch.arange(n_lead_units, dtype=torch.int64) * u, lead + torch.arange(n_rest_units, dtype=torch.int64) * u])
+    stop = torch.cat([torch.clamp(start[:n_lead_units] + u, max=lead), torch.clamp(start[n_lead_units:] + u, max=nc)])
+    o = torch.argsort(key, stable=True)
+    start, stop = start[o], stop[o]
+    lens = stop - start
+    off = torch.cumsum(lens, 0) - lens
+    perm = (torch.repeat_interleave(start - off, lens) + torch.arange(nc, dtype=torch.int64)).to(dev)
+    W = plan.chunk_edges
+    cols = plan.cols.view(nc, W)[perm].contiguous().view(-1)
+    vals = None if plan.vals is None else plan.vals.view(nc, W)[perm].contiguous().view(-1)
+    out = StreamPlan(plan.n, plan.nnz, W, nc, cols, vals, plan.seg_row, plan.chunk_seg[perm].contiguous(), plan.fix_ptr,
+                     plan.fix_row, plan.fix_deg, plan.n_slots, plan.order, plan.n_segs_real, plan.row_deg,
+                     plan.wide_cta, plan.lane_group, plan.carve)
+    return out
+
+
 def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=512, n_blocks=64, min_piece=4,
-                      wide_cta=True):
+                      wide_cta=True, interleave=False, unit_chunks=64):
     """Edge stream with the hot column blocks carved out ("carved stream").
 
     Columns are ranked by degree; block b holds the columns of rank [b * block_cols, (b+1) * block_cols)
@@ -275,7 +310,8 @@ def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=51
     that an SM walking consecutive chunks keeps gathering the same ``block_cols`` rows.  What is left
     of every row follows in degree order, exactly as in ``build_stream_plan(order=degree_order)``.
     Every carved row becomes a split row (partial sums + fix-up), results are order-deterministic.
-    Column ids are not relabelled.
+    Column ids are not relabelled.  ``interleave=True`` alternates units of ``unit_chunks`` carved chunks
+    with units of residual chunks (``interleave_chunks``).
     """
     if chunk_edges % 128 != 0 or chunk_edges <= 0:
         raise ValueError("chunk_edges must be a positive multiple of 128")
@@ -317,7 +353,10 @@ def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=51
     plan = _plan_from_runs(n, run_row, run_len, stream_cols, stream_vals, chunk_edges, deg, rank, order)
     plan.wide_cta = bool(wide_cta)
     plan.carve = {"block_cols": block_cols, "n_blocks": NB, "min_piece": min_piece, "carved_edges": carved_edges,
-                  "carved_pieces": n_carved_runs, "n_slots": plan.n_slots, "n_fix": plan.n_fix}
+                  "carved_pieces": n_carved_runs, "n_slots": plan.n_slots, "n_fix": plan.n_fix,
+                  "interleave": bool(interleave)}
+    if interleave:
+        plan = interleave_chunks(plan, carved_edges // chunk_edges, unit_chunks)
     return plan
 
 

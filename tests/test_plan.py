@@ -199,3 +199,25 @@ def test_lane_transposed_layout_walks_to_the_same_result(G):
 
 def test_lane_group_for_matches_dispatch():
     assert [lane_group_for(F) for F in (64, 16, 32, 128, 256, 7, 3, 1, 48)] == [16, 4, 8, 32, 32, 8, 4, 1, 16]
+
+
+def test_interleaved_carved_stream_is_a_chunk_permutation_with_the_same_result():
+    ah, ip, idx, val = ahat_tensors("cora_ml")
+    H = np.random.RandomState(5).randn(ah.shape[0], 2)
+    a = build_carved_plan(ip, idx, val, 128, 64, 8, 3)
+    b = build_carved_plan(ip, idx, val, 128, 64, 8, 3, interleave=True, unit_chunks=4)
+    assert b.carve["interleave"] and not torch.equal(a.cols, b.cols)
+    ca, cb = a.cols.view(a.n_chunks, 128), b.cols.view(b.n_chunks, 128)
+    # same multiset of chunks, each still pointing at its own segments
+    ka = sorted(zip(a.chunk_seg.tolist(), [tuple(r) for r in ca.tolist()]))
+    kb = sorted(zip(b.chunk_seg.tolist(), [tuple(r) for r in cb.tolist()]))
+    assert ka == kb
+    # carved and residual units alternate: the first residual chunk comes long before the last carved one
+    lead = a.carve["carved_edges"] // 128
+    where = {tuple(r): i for i, r in enumerate(cb.tolist())}
+    real = (a.nnz + 127) // 128                      # chunks after this one are identical padding
+    pos = np.array([where[tuple(r)] for r in ca.tolist()[:real]])
+    assert pos[lead:].min() < pos[:lead].max() and (np.diff(pos[:lead]) > 0).all() and (np.diff(pos[lead:]) > 0).all()
+    za = walk_stream(a, H, H, 0.1, 0, True)
+    zb = walk_stream(b, H, H, 0.1, 0, True)
+    assert np.array_equal(za, zb)

@@ -22,6 +22,9 @@ VARIANTS = [
     ("carve512x64+idx16", dict(order="carve", idx16=True, carve=dict(block_cols=512, n_blocks=64, min_piece=4))),
     ("carve512x256+idx16", dict(order="carve", idx16=True, carve=dict(block_cols=512, n_blocks=256, min_piece=4))),
     ("carve384x96T6+idx16", dict(order="carve", idx16=True, carve=dict(block_cols=384, n_blocks=96, min_piece=6))),
+    # not measured in round 1 (GPU budget spent): carved and residual chunk units alternating
+    ("carve512x64T8+idx16+interleave", dict(order="carve", idx16=True, carve=dict(block_cols=512, n_blocks=64, min_piece=8, interleave=True))),
+    ("carve512x64T4+idx16+interleave", dict(order="carve", idx16=True, carve=dict(block_cols=512, n_blocks=64, min_piece=4, interleave=True))),
 ]
 
 

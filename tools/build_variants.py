@@ -13,6 +13,9 @@ VARIANTS = {
     "mb3_u8": ["PPNP_SPMM_MINBLOCKS=3", "PPNP_SPMM_U4=8"],
     "mb2_u8": ["PPNP_SPMM_MINBLOCKS=2", "PPNP_SPMM_U4=8"],
     "mb4_u2": ["PPNP_SPMM_MINBLOCKS=4", "PPNP_SPMM_U4=2"],
+    # slabs with <= 2 segment ends per lane group keep the rolling gather ring (profiles/r01_variants.md, point 3)
+    "fewends": ["PPNP_SPMM_FEWENDS=1"],
+    "fewends_segpred": ["PPNP_SPMM_FEWENDS=1", "PPNP_SPMM_SEGPRED=1"],
 }
 
 if __name__ == "__main__":
