@@ -252,7 +252,9 @@ def run_ours(args):
         from ppnp_b200 import dist as pd
         result = pd.bench_partitioned(wl, n, raw, scale, F, KSTEPS, ALPHA, steps, warmup, dev, rank, world,
                                        phases=args.phases, transport=args.transport, stripes=args.stripes,
-                                       row_groups=args.row_groups)
+                                       row_groups=args.row_groups,
+                                       carve=({"block_cols": args.carve_block_cols, "n_blocks": args.carve_blocks,
+                                               "min_piece": args.carve_min_piece} if args.order == "carve" else None))
         if rank == 0:
             sampler_clocks = result.pop("clocks")
             nnz = result.pop("nnz")

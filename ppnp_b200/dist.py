@@ -687,9 +687,12 @@ class FusedPushPropagation:
 
     MAX_PEERS = 8
 
-    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, group=None, step_fn=None):
+    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, group=None, step_fn=None, carve=None):
+        """carve: keyword arguments of plan.build_carved_plan (block_cols, n_blocks, min_piece): stream the
+        shard with its hot column blocks first (blocks sized for the L2: the cold gathers of the hub rows
+        stay inside an L2-resident window) instead of in plain degree order."""
         import ctypes as C
-        from .plan import build_stream_plan
+        from .plan import build_carved_plan, build_stream_plan
         self.topo, self.group, self._step_fn = topo, group, step_fn
         dev = topo.indices.device
         self.on_gpu = dev.type == "cuda"
@@ -703,8 +706,13 @@ class FusedPushPropagation:
         row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), deg)
         vals = dinv_ext[row_of] * dinv_ext[topo.indices.to(torch.int64)]
         del row_of
-        order = torch.sort(deg, descending=True, stable=True).indices
-        self.sub = _SubGraph(build_stream_plan(ip, topo.indices, vals, chunk_edges, order), step_fn)
+        if carve:
+            plan = build_carved_plan(ip, topo.indices, vals, chunk_edges, n_cols=n_local + topo.n_halo, wide_cta=False,
+                                     **carve)
+        else:
+            order = torch.sort(deg, descending=True, stable=True).indices
+            plan = build_stream_plan(ip, topo.indices, vals, chunk_edges, order)
+        self.sub = _SubGraph(plan, step_fn)
         self.plans = [self.sub]
         del vals
         # push lists: for every local row, the (peer, slot) pairs that want it
@@ -1004,7 +1012,8 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
     return 1.0 / torch.sqrt(out)
 
 
-def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4):
+def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4,
+                      carve=None):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
@@ -1015,9 +1024,11 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
+    if carve and not (transport in ("auto", "fused") and world > 1):
+        raise ValueError("carved shard streams exist for the fused transport (--transport fused, N > 1)")
     if transport in ("auto", "fused") and world > 1:
         try:
-            prop = FusedPushPropagation(topo, dinv)
+            prop = FusedPushPropagation(topo, dinv, carve=carve)
             prop.alloc(4, 1)                                  # peer mappings must be obtainable on this box
         except Exception as e:  # noqa: BLE001
             if transport == "fused":

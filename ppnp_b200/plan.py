@@ -300,7 +300,7 @@ def interleave_chunks(plan: StreamPlan, n_lead_chunks, unit_chunks=64):
 
 
 def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=512, n_blocks=64, min_piece=4,
-                      wide_cta=True, interleave=False, unit_chunks=64):
+                      wide_cta=True, interleave=False, unit_chunks=64, n_cols=None):
     """Edge stream with the hot column blocks carved out ("carved stream").
 
     Columns are ranked by degree; block b holds the columns of rank [b * block_cols, (b+1) * block_cols)
@@ -311,7 +311,11 @@ def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=51
     of every row follows in degree order, exactly as in ``build_stream_plan(order=degree_order)``.
     Every carved row becomes a split row (partial sums + fix-up), results are order-deterministic.
     Column ids are not relabelled.  ``interleave=True`` alternates units of ``unit_chunks`` carved chunks
-    with units of residual chunks (``interleave_chunks``).
+    with units of residual chunks (``interleave_chunks``).  ``n_cols``: width of the column space when it is
+    not the row count (a shard of the partitioned form: local rows x [local | halo] columns); columns are
+    ranked by how many stored entries reference them -- for the symmetric A_hat that IS the row degree.
+    With blocks sized for the L2 instead of the L1 (e.g. 16 blocks of n/16 columns) the same stream keeps the
+    cold gathers of the hub rows inside an L2-resident window (oracle/l1sim.c with one cache models it).
     """
     if chunk_edges % 128 != 0 or chunk_edges <= 0:
         raise ValueError("chunk_edges must be a positive multiple of 128")
@@ -329,9 +333,20 @@ def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=51
     order = degree_order(indptr)
     rank = torch.empty(n, dtype=torch.int64, device=dev)
     rank[order] = torch.arange(n, device=dev, dtype=torch.int64)
-    NB = int(min(n_blocks, (n + block_cols - 1) // block_cols))
+    m_cols = n if n_cols is None else int(n_cols)
+    if m_cols == n and n_cols is None:
+        crank = rank                     # symmetric pattern: references per column == row degree
+    else:
+        if nnz and int(indices.max().item()) >= m_cols:
+            raise ValueError("a column index lies outside n_cols")
+        refs = torch.bincount(indices.to(torch.int64), minlength=m_cols)
+        corder = torch.sort(refs, descending=True, stable=True).indices
+        crank = torch.empty(m_cols, dtype=torch.int64, device=dev)
+        crank[corder] = torch.arange(m_cols, device=dev, dtype=torch.int64)
+        del refs, corder
+    NB = int(min(n_blocks, (m_cols + block_cols - 1) // block_cols))
     row_of = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), deg)
-    blk = torch.div(rank[indices.to(torch.int64)], block_cols, rounding_mode="floor").clamp_(max=NB)
+    blk = torch.div(crank[indices.to(torch.int64)], block_cols, rounding_mode="floor").clamp_(max=NB)
     # edges per (row, block): CSR order is row-major, so a stable sort by block inside the row groups them
     key = row_of * (NB + 1) + blk
     skey, perm = torch.sort(key, stable=True)

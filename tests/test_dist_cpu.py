@@ -72,13 +72,17 @@ def worker(rank, world, port, phases, outdir):
         assert np.allclose(dinv.numpy(), 1 / np.sqrt(odeg))
         if phases == "fused":
             prop = pd.FusedPushPropagation(topo, dinv, chunk_edges=128, step_fn=walker_step)
+        elif phases == "fused-carve":      # hot column blocks of the shard's [local | halo] column space first
+            prop = pd.FusedPushPropagation(topo, dinv, chunk_edges=128, step_fn=walker_step,
+                                           carve=dict(block_cols=100, n_blocks=6, min_piece=3))
+            assert prop.sub.plan.carve["carved_edges"] > 0 and not prop.sub.plan.wide_cta
         elif phases.startswith("pipe"):
             prop = pd.PipelinedPushPropagation(topo, dinv, chunk_edges=128, row_groups=int(phases[4:]), step_fn=walker_step)
         else:
             prop = pd.PartitionedPropagation(topo, dinv, chunk_edges=128, phases=phases, step_fn=walker_step)
         rng = np.random.RandomState(0)
         Hg = rng.randn(n, F).astype(np.float32)                                # the same global H on every rank
-        n_ext = prop.rows_alloc if (phases.startswith("pipe") or phases == "fused") else prop.n_ext()
+        n_ext = prop.rows_alloc if (phases.startswith("pipe") or phases.startswith("fused")) else prop.n_ext()
         H = torch.zeros(n_ext, F); H[: topo.n_local] = torch.from_numpy(Hg[lo:hi])
         Z, S = torch.zeros_like(H), torch.zeros_like(H)
         out = prop.propagate(H, Z, S, K, alpha)
@@ -96,7 +100,8 @@ def worker(rank, world, port, phases, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,phases", [(2, "peer"), (2, "one"), (3, "peer"), (3, "two"), (2, "pipe3"), (3, "pipe4"), (3, "pipe1"), (2, "fused"), (3, "fused")])
+@pytest.mark.parametrize("world,phases", [(2, "peer"), (2, "one"), (3, "peer"), (3, "two"), (2, "pipe3"), (3, "pipe4"), (3, "pipe1"), (2, "fused"), (3, "fused"),
+                                          (2, "fused-carve"), (3, "fused-carve")])
 def test_partitioned_propagation_gloo(tmp_path, world, phases):
     port = 29600 + world * 10 + len(phases) + (os.getpid() % 50)
     mp.spawn(worker, args=(world, port, phases, str(tmp_path)), nprocs=world, join=True)
