@@ -44,6 +44,7 @@ SIGNATURES = {
     "ppnp_appnp_propagate": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32, _f32, _i32, _i32, _p]),
     "ppnp_appnp_propagate_persistent": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32, _f32, _p]),
     "ppnp_ppr_dense": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),
+    "ppnp_ppr_dense_cheb": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),
     "ppnp_gather_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _i32, _p, _i64, _i32, _p]),
     "ppnp_gather_gemm_bf16_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "ppnp_gather_gemm_bf16": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _i32, _p, _i64, _p, _i64, _p]),

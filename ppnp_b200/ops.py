@@ -211,13 +211,41 @@ def ppr_steps_for_tol(alpha, tol):
     return max(1, int(math.ceil(math.log(tol) / math.log(1.0 - alpha))))
 
 
-def ppr_dense(ahat: NormalizedCSR, alpha, K=None, tol=1e-7):
+def ppr_cheb_steps_for_tol(alpha, tol):
+    """Steps of the Chebyshev-accelerated iteration for error ``tol``: 2 s^K / (1 + s^2K) <= tol with
+    s = (1 - sqrt(1 - rho^2)) / rho, rho = 1 - alpha (plus a margin of 4 steps: fp32 round-off floor)."""
+    import math
+    rho = 1.0 - alpha
+    s = (1.0 - math.sqrt(1.0 - rho * rho)) / rho
+    k = 1
+    while 2.0 * s ** k / (1.0 + s ** (2 * k)) > tol:
+        k += 1
+    return k + 4
+
+
+def ppr_dense(ahat: NormalizedCSR, alpha, K=None, tol=1e-7, method="power"):
     """helpers.py:68-71 ``compute_ppr``: Pi = alpha (I - (1-alpha) A_hat)^-1 as a dense fp32 n x n
-    CUDA tensor, by power iteration on all n right-hand sides (csrc/ppr_dense.cu)."""
+    CUDA tensor, by iteration on all n right-hand sides (csrc/ppr_dense.cu): ``method="power"`` is the
+    plain fixed point (error (1-alpha)^K), ``"chebyshev"`` its Chebyshev acceleration (~4x fewer steps at
+    alpha = 0.1, same bytes per step)."""
     lib = _lib.load()
     if ahat.val32 is None:
         raise ValueError("ppr_dense needs the fp32 values of A_hat")
+    if method not in ("power", "chebyshev"):
+        raise ValueError(f"unknown method {method!r}")
     n = ahat.n
+    if method == "chebyshev":
+        K = ppr_cheb_steps_for_tol(alpha, tol) if K is None else int(K)
+        if K < 1:
+            raise ValueError("the Chebyshev iteration needs K >= 1")
+        dev = ahat.indices.device
+        Pi = torch.empty((n, n), dtype=torch.float32, device=dev)
+        scratch = torch.empty((n, n), dtype=torch.float32, device=dev) if K > 1 else None
+        with torch.cuda.device(dev):
+            rc = lib.ppnp_ppr_dense_cheb(_lib.ptr(ahat.indptr), _lib.ptr(ahat.indices), _lib.ptr(ahat.val32), n,
+                                         float(alpha), K, _lib.ptr(Pi), _lib.ptr(scratch), _lib.current_stream())
+        _lib.check(rc, "ppnp_ppr_dense_cheb")
+        return Pi
     K = ppr_steps_for_tol(alpha, tol) if K is None else int(K)
     dev = ahat.indices.device
     Pi = torch.empty((n, n), dtype=torch.float32, device=dev)

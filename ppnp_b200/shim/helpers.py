@@ -19,6 +19,7 @@ Environment switches (main.py has no flag for them and stays unchanged):
                               records the normalised graph for model.PPNP and returns a placeholder
   PPNP_K                      APPNP steps (default 10)
   PPNP_PPR_TOL                stop tolerance of the power iteration building Pi (default 1e-7)
+  PPNP_PPR_METHOD = power | chebyshev   plain fixed point (default) or its Chebyshev acceleration
 """
 import os
 import random
@@ -113,7 +114,7 @@ def compute_ppr(adj, alpha, mode="sym"):
     if os.environ.get("PPNP_MODE", "exact").lower() == "appnp":
         return np.zeros((1, 1), dtype=np.float32)          # placeholder; model.PPNP propagates on the graph
     tol = float(os.environ.get("PPNP_PPR_TOL", "1e-7"))
-    Pi = _P.ppr_dense(ahat, float(alpha), tol=tol)
+    Pi = _P.ppr_dense(ahat, float(alpha), tol=tol, method=os.environ.get("PPNP_PPR_METHOD", "power"))
     host = torch.empty(Pi.shape, dtype=torch.float32, pin_memory=True)
     host.copy_(Pi)
     torch.cuda.synchronize()

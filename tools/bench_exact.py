@@ -40,10 +40,15 @@ def main():
     ahat = P.csr_normalize(ip, idx)
     K = P.ppr_steps_for_tol(alpha, 1e-7)
     t_build = timed(lambda: P.ppr_dense(ahat, alpha, K=K), reps=3, warm=1)
+    Kc = P.ppr_cheb_steps_for_tol(alpha, 1e-7)
+    t_cheb = timed(lambda: P.ppr_dense(ahat, alpha, K=Kc, method="chebyshev"), reps=3, warm=1)
+    Pc = P.ppr_dense(ahat, alpha, K=Kc, method="chebyshev")
     Pi = P.ppr_dense(ahat, alpha, K=K)
     out = {"what": "ppr_build", "n": n, "nnz_a": int(ip[-1]), "K": K, "ms": t_build,
            "algorithmic_GB": 3 * n * n * 4 * K / 1e9, "achieved_GBps": 3 * n * n * 4 * K / 1e9 / (t_build * 1e-3),
-           "frac_of_hbm_peak": 3 * n * n * 4 * K / 1e9 / (t_build * 1e-3) / PEAK}
+           "frac_of_hbm_peak": 3 * n * n * 4 * K / 1e9 / (t_build * 1e-3) / PEAK,
+           "chebyshev": {"K": Kc, "ms": t_cheb, "rel_diff_vs_power": float((Pc - Pi).norm() / Pi.norm())}}
+    del Pc
     # CPU reference sample: helpers.py:68-71 on the first ns nodes' induced subgraph is not the same
     # matrix; time the dense fp64 inverse itself at a bounded size and quote the n^3 scaling
     ns = int(os.environ.get("PPNP_CPU_INV_N", "5000"))
