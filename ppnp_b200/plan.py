@@ -300,7 +300,7 @@ def interleave_chunks(plan: StreamPlan, n_lead_chunks, unit_chunks=64):
 
 
 def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=512, n_blocks=64, min_piece=4,
-                      wide_cta=True, interleave=False, unit_chunks=64, n_cols=None):
+                      wide_cta=True, interleave=False, unit_chunks=64, n_cols=None, levels=None):
     """Edge stream with the hot column blocks carved out ("carved stream").
 
     Columns are ranked by degree; block b holds the columns of rank [b * block_cols, (b+1) * block_cols)
@@ -316,11 +316,17 @@ def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=51
     ranked by how many stored entries reference them -- for the symmetric A_hat that IS the row degree.
     With blocks sized for the L2 instead of the L1 (e.g. 16 blocks of n/16 columns) the same stream keeps the
     cold gathers of the hub rows inside an L2-resident window (oracle/l1sim.c with one cache models it).
+    ``levels`` = [(block_cols, n_blocks, min_piece), ...] stacks several block sizes along the rank axis
+    (e.g. 64 L1-sized blocks over the hottest columns, then L2-sized blocks over the rest) and replaces
+    the three scalar parameters.
     """
     if chunk_edges % 128 != 0 or chunk_edges <= 0:
         raise ValueError("chunk_edges must be a positive multiple of 128")
-    if block_cols <= 0 or n_blocks < 0 or min_piece < 1:
-        raise ValueError("block_cols > 0, n_blocks >= 0, min_piece >= 1")
+    if levels is None:
+        levels = [(block_cols, n_blocks, min_piece)]
+    for bc_, nb_, t_ in levels:
+        if bc_ <= 0 or nb_ < 0 or t_ < 1:
+            raise ValueError("block_cols > 0, n_blocks >= 0, min_piece >= 1")
     dev = indices.device
     n = int(indptr.numel()) - 1
     ip = indptr.to(torch.int64)
@@ -344,14 +350,23 @@ def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=51
         crank = torch.empty(m_cols, dtype=torch.int64, device=dev)
         crank[corder] = torch.arange(m_cols, device=dev, dtype=torch.int64)
         del refs, corder
-    NB = int(min(n_blocks, (m_cols + block_cols - 1) // block_cols))
+    ends, tmins = [], []                 # block b = ranks [ends[b-1], ends[b]), carved from pieces of >= tmins[b] edges
+    for bc_, nb_, t_ in levels:
+        for _ in range(int(nb_)):
+            lo = ends[-1] if ends else 0
+            if lo >= m_cols:
+                break
+            ends.append(min(lo + int(bc_), m_cols))
+            tmins.append(int(t_))
+    NB = len(ends)
     row_of = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), deg)
-    blk = torch.div(crank[indices.to(torch.int64)], block_cols, rounding_mode="floor").clamp_(max=NB)
+    blk = torch.bucketize(crank[indices.to(torch.int64)], torch.tensor(ends, dtype=torch.int64, device=dev), right=True)
+    tmin = torch.tensor(tmins + [1 << 62], dtype=torch.int64, device=dev)
     # edges per (row, block): CSR order is row-major, so a stable sort by block inside the row groups them
     key = row_of * (NB + 1) + blk
     skey, perm = torch.sort(key, stable=True)
     _, inv, cnt = torch.unique_consecutive(skey, return_inverse=True, return_counts=True)
-    keep = (cnt[inv] >= min_piece) & ((skey % (NB + 1)) < NB)
+    keep = (cnt[inv] >= tmin[skey % (NB + 1)]) & ((skey % (NB + 1)) < NB)
     fblk = torch.full((nnz,), NB, dtype=torch.int64, device=dev)
     fblk[perm] = torch.where(keep, skey % (NB + 1), torch.full_like(skey, NB))
     carved_edges = int(keep.sum().item())
@@ -367,7 +382,8 @@ def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=51
     del key2, skey2, perm2, fblk, row_of
     plan = _plan_from_runs(n, run_row, run_len, stream_cols, stream_vals, chunk_edges, deg, rank, order)
     plan.wide_cta = bool(wide_cta)
-    plan.carve = {"block_cols": block_cols, "n_blocks": NB, "min_piece": min_piece, "carved_edges": carved_edges,
+    plan.carve = {"block_cols": levels[0][0], "n_blocks": NB, "min_piece": levels[0][2],
+                  "levels": [list(map(int, lv)) for lv in levels], "carved_edges": carved_edges,
                   "carved_pieces": n_carved_runs, "n_slots": plan.n_slots, "n_fix": plan.n_fix,
                   "interleave": bool(interleave)}
     if interleave:

@@ -221,3 +221,20 @@ def test_interleaved_carved_stream_is_a_chunk_permutation_with_the_same_result()
     za = walk_stream(a, H, H, 0.1, 0, True)
     zb = walk_stream(b, H, H, 0.1, 0, True)
     assert np.array_equal(za, zb)
+
+
+def test_two_level_carve_blocks_stack_along_the_rank_axis():
+    ah, ip, idx, val = ahat_tensors("cora_ml")
+    H = np.random.RandomState(6).randn(ah.shape[0], 2)
+    one = build_carved_plan(ip, idx, val, 128, 32, 4, 3)
+    same = build_carved_plan(ip, idx, val, 128, levels=[(32, 4, 3)])
+    assert torch.equal(one.cols, same.cols) and torch.equal(one.seg_row, same.seg_row)
+    two = build_carved_plan(ip, idx, val, 128, levels=[(32, 4, 3), (500, 3, 6)])
+    assert two.carve["n_blocks"] == 7 and two.carve["carved_edges"] > one.carve["carved_edges"]
+    # carved part: block index never decreases; blocks 0-3 are 32 ranks wide, 4-6 are 500 wide
+    order = degree_order(ip).numpy()
+    rank = np.empty(two.n, dtype=np.int64); rank[order] = np.arange(two.n)
+    r = rank[two.cols.numpy()[:two.carve["carved_edges"]] & 0x7FFFFFFF]
+    blk = np.where(r < 128, r // 32, 4 + (r - 128) // 500)
+    assert (np.diff(blk) >= 0).all() and blk.max() == 6
+    assert relerr(walk_stream(two, H, H, 0.1, 0, True), oracle.appnp(ah, H, 0.1, 1)) < 1e-7

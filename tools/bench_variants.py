@@ -24,6 +24,9 @@ VARIANTS = [
     ("carve384x96T6+idx16", dict(order="carve", idx16=True, carve=dict(block_cols=384, n_blocks=96, min_piece=6))),
     # not measured in round 1 (GPU budget spent): carved and residual chunk units alternating
     ("carve512x64T8+idx16+interleave", dict(order="carve", idx16=True, carve=dict(block_cols=512, n_blocks=64, min_piece=8, interleave=True))),
+    ("carve2level+idx16+interleave", dict(order="carve", idx16=True, carve=dict(levels=[(512, 64, 8), (125000, 16, 16)], interleave=True))),
+    ("carve2level+idx16", dict(order="carve", idx16=True, carve=dict(levels=[(512, 64, 8), (125000, 16, 16)]))),
+    ("carveL2only+idx16", dict(order="carve", idx16=True, carve=dict(levels=[(125000, 16, 16)], wide_cta=False))),
     ("carve512x64T4+idx16+interleave", dict(order="carve", idx16=True, carve=dict(block_cols=512, n_blocks=64, min_piece=4, interleave=True))),
 ]
 

@@ -6,6 +6,9 @@ on the CPU) and feeds their column stream to the LRU model oracle/l1sim.c:
   python tools/carve_model.py l1     per-SM L1 (148 SMs, units of 64 chunks): rows crossing L2 -> SM
   python tools/carve_model.py l2     one shared cache: rows crossing HBM -> L2, for 256-byte rows (config 4,
                                      96 MB) and for the config-5 scale model (64-byte rows, cache / 8)
+  python tools/carve_model.py l12    per-SM L1 (512 rows) in front of a shared L2 (375 k rows): one- and
+                                     two-level carves (L1-sized blocks over the hottest columns, L2-sized
+                                     blocks over the rest), with and without chunk interleaving
 
 Round-1 output is quoted in profiles/r01_variants.md and DESIGN.md section 8.
 """
@@ -25,12 +28,13 @@ from ppnp_b200.plan import build_carved_plan, build_stream_plan, degree_order  #
 SIM = os.path.join(ROOT, "oracle", "_build", "l1sim")
 
 
-def misses(plan, cache_rows, sms, unit):
+def misses(plan, cache_rows, sms, unit, l2_rows=0):
     tmp = "/tmp/carve_model_cols.i32"
     plan.cols.numpy().tofile(tmp)
-    out = subprocess.run([SIM, tmp, str(plan.n_chunks), str(plan.chunk_edges), str(plan.n), str(cache_rows), str(sms), str(unit)],
-                         capture_output=True, text=True, check=True).stdout
-    return int(out.split("L1 misses")[1].split("(")[0])
+    out = subprocess.run([SIM, tmp, str(plan.n_chunks), str(plan.chunk_edges), str(plan.n), str(cache_rows), str(sms), str(unit)] +
+                         ([str(l2_rows)] if l2_rows else []), capture_output=True, text=True, check=True).stdout
+    m1 = int(out.split("L1 misses")[1].split("(")[0])
+    return (m1, int(out.split("L2 misses")[1].split("(")[0])) if l2_rows else m1
 
 
 def main():
@@ -49,6 +53,16 @@ def main():
                 print(f"carve {bc}x{nb} min piece {t}, L1 {rows} rows: carved {100 * p.carve['carved_edges'] / p.nnz:.1f}% in "
                       f"{p.carve['carved_pieces'] / 1e6:.2f} M pieces, {100 * misses(p, rows, 148, 64) / p.nnz:.1f}% of the edges cross "
                       f"L2 -> SM (+{100 * p.n_slots / p.nnz:.1f}% partial reads)", flush=True)
+    elif mode == "l12":
+        cases = [("degree order", base),
+                 ("carve 512x64 min 8", build_carved_plan(tip, tidx, None, 256, 512, 64, 8)),
+                 ("carve 512x64 min 8, interleaved", build_carved_plan(tip, tidx, None, 256, 512, 64, 8, interleave=True)),
+                 ("carve 512x64 min 8 + 125k x 16 min 16", build_carved_plan(tip, tidx, None, 256, levels=[(512, 64, 8), (125_000, 16, 16)])),
+                 ("carve 512x128 min 6 + 250k x 8 min 16", build_carved_plan(tip, tidx, None, 256, levels=[(512, 128, 6), (250_000, 8, 16)]))]
+        for tag, p in cases:
+            m1, m2 = misses(p, 512, 148, 64, 375_000)
+            print(f"{tag}: {100 * m1 / p.nnz:.1f}% of the edges cross L2 -> SM, {m2 / 1e6:.2f} M rows come from HBM, "
+                  f"{p.n_slots / 1e6:.2f} M partial rows", flush=True)
     else:
         for cache_rows, tag in ((190_000, "config-5 scale model: 64-byte rows, cache / 8"), (375_000, "config 4: 256-byte rows, 96 MB")):
             m = misses(base, cache_rows, 1, 64)
