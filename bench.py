@@ -288,6 +288,8 @@ def run_ours(args):
     if args.order == "carve":
         carve = {"block_cols": args.carve_block_cols, "n_blocks": args.carve_blocks, "min_piece": args.carve_min_piece,
                  "wide_cta": not args.carve_narrow_cta, "interleave": args.carve_interleave}
+        if args.carve_levels:      # "512x64x8,125000x16x16": block_cols x n_blocks x min_piece per level
+            carve["levels"] = [tuple(int(v) for v in lv.split("x")) for lv in args.carve_levels.split(",")]
     graph = P.PropagationGraph(ahat, chunk_edges=args.chunk_edges, order=args.order, idx16=args.idx16, carve=carve)
     nnz = ahat.nnz
     torch.cuda.synchronize()
@@ -442,6 +444,7 @@ def main():
     ap.add_argument("--carve-min-piece", type=int, default=4, help="--order carve: smallest (row, block) piece taken out of its row")
     ap.add_argument("--carve-narrow-cta", action="store_true", help="--order carve: keep the 256-thread CTAs")
     ap.add_argument("--carve-interleave", action="store_true", help="--order carve: alternate carved and residual chunk units")
+    ap.add_argument("--carve-levels", default=None, help="--order carve: stacked block levels, e.g. 512x64x8,125000x16x16")
     ap.add_argument("--chunk-edges", type=int, default=256)
     ap.add_argument("--use-vals", action="store_true", help="stored-value form in every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
