@@ -42,6 +42,10 @@ extern "C" {
  * contribution to rows an earlier pass already wrote (multi-pass steps of the partitioned form,
  * ppnp_b200/dist.py: local columns first, halo columns once they have arrived). */
 #define PPNP_EPI_ACC 16
+/* OR-ed onto PPNP_EPI_ACC: Zin may be the output buffer itself.  The caller guarantees that the rows the
+ * stream GATHERS are not rows it produces (the hub-combine launch of ppnp_b200/dist.py HybridPushPropagation:
+ * it gathers the partial-row slots of the buffer and adds them to hub rows of the same buffer). */
+#define PPNP_EPI_INPLACE 32
 
 /* peers addressable by the fused halo push (ppnp_spmm_step_push): ranks of one NVSwitch domain */
 #define PPNP_MAX_PEERS 8

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("PPNP_B200_LIB") or os.path.join(_HERE, "libppnp_b200.
 MODE_SYM, MODE_RW = 0, 1
 EPI_PLAIN, EPI_Z2Y, EPI_Y, EPI_Y2Z, EPI_RW = 0, 1, 2, 3, 4
 EPI_ACC = 16
+EPI_INPLACE = 32
 STD_UNDIRECTED, STD_NO_SELF_LOOPS, STD_LCC = 1, 2, 4
 FLAG = 0x80000000
 

@@ -798,12 +798,13 @@ int ppnp_spmm_step(const ppnp_plan_t* plan, const float* Zin, const float* T, fl
     int rc = validate_plan(plan);
     if (rc) return rc;
     PPNP_REQUIRE(Zin && T && Zout, "null matrix pointer");
-    PPNP_REQUIRE(Zin != Zout, "Zout must not alias Zin");
+    PPNP_REQUIRE(Zin != Zout || (epi & PPNP_EPI_INPLACE), "Zout must not alias Zin (unless PPNP_EPI_INPLACE)");
     PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
-    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~31) == 0, "bad epilogue");
+    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~63) == 0, "bad epilogue");
     PPNP_REQUIRE(!(epi & PPNP_EPI_ACC) || T == Zout, "PPNP_EPI_ACC adds to the output: pass T == Zout");
+    PPNP_REQUIRE(!(epi & PPNP_EPI_INPLACE) || (epi & PPNP_EPI_ACC), "PPNP_EPI_INPLACE goes with PPNP_EPI_ACC");
     PushArgs none{};
     return dispatch_step(plan, Zin, T, Zout, partial, ld, F, alpha, epi, use_vals != 0, none, as_stream(stream));
 }
@@ -855,11 +856,11 @@ int ppnp_spmm_step_push(const ppnp_plan_t* plan, const float* Zin, const float* 
     int rc = validate_plan(plan);
     if (rc) return rc;
     PPNP_REQUIRE(Zin && T && Zout, "null matrix pointer");
-    PPNP_REQUIRE(Zin != Zout, "Zout must not alias Zin");
+    PPNP_REQUIRE(Zin != Zout || (epi & PPNP_EPI_INPLACE), "Zout must not alias Zin (unless PPNP_EPI_INPLACE)");
     PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
-    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~31) == 0, "bad epilogue");
+    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~63) == 0, "bad epilogue");
     PPNP_REQUIRE(push_ptr == nullptr || (push_code && push_first && peer_bases_host && n_peers >= 1 && n_peers <= PPNP_MAX_PEERS),
                  "push lists need codes, the per-row summary and 1..PPNP_MAX_PEERS peer base pointers");
     PushArgs pa{};

@@ -887,6 +887,287 @@ class FusedPushPropagation:
         return Z_ext[: t.n_local]
 
 
+def _push_arrays(n_rows, rows, codes, dev):
+    """Per-row push lists in the layout the kernel epilogue reads (csrc/appnp_spmm.cu PushArgs):
+    ptr[n_rows + 1] ranges into code[], first[r] = -1 none / >= 0 the only destination / -2 several."""
+    if rows.numel():
+        perm = torch.sort(rows, stable=True).indices
+        rows, codes = rows[perm], codes[perm]
+        cnt = torch.bincount(rows, minlength=n_rows)
+    else:
+        cnt = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+    pp = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+    pp[1:] = torch.cumsum(cnt, 0)
+    first = torch.full((n_rows,), -1, dtype=torch.int64, device=dev)
+    if rows.numel():
+        one = cnt == 1
+        first[one] = codes[pp[:-1][one]]
+        first[cnt > 1] = -2
+    code = torch.cat([codes.to(torch.int64), torch.zeros(1, dtype=torch.int64, device=dev)])
+    return {"ptr": pp.to(torch.int32).contiguous(), "code": code.to(torch.int32).contiguous(),
+            "first": first.to(torch.int32).contiguous(), "rows": rows, "codes": codes.to(torch.int64)}
+
+
+class HybridPushPropagation:
+    """Fused-push propagation in which HUB rows are computed where their columns live.
+
+    A row of degree >= ``hub_degree`` keeps only its LOCAL columns at its owner.  Every other rank sums
+    the columns it owns into one partial row per such hub (a *virtual row* of its own stream -- by the
+    symmetry of the pattern it finds those edges in its own rows) and the kernel epilogue stores that
+    partial into a slot of the owner's buffer over NVLink, exactly like a halo row.  After a rank barrier a
+    second, small launch of the same kernel (accumulate epilogue, PPNP_EPI_ACC | PPNP_EPI_INPLACE) adds the
+    received partials to the hub rows, finishes them and pushes them to the ranks that reference them; a
+    second barrier ends the step.  The owner's halo then holds only what its non-hub rows reference:
+    tools/halo_model.py puts the rows a rank receives per step at ~62 % of the 1-D form at 8 ranks.
+
+    Buffer rows: [local | virtual rows (outputs only) | halo | partial slots].  Everything is built from the
+    kernel features the 1-D form already uses (partial-row streams with a per-row degree, the accumulate
+    epilogue, push lists); the virtual rows get the "degree" that makes their epilogue the identity
+    ((1-alpha) for the 1/d epilogues, (1-alpha)^2 for the 1/sqrt(d) ones) and a zero teleport row.
+    Host logic is covered under gloo (tests/test_dist_cpu.py); not yet measured on GPUs."""
+
+    MAX_PEERS = 8
+
+    def __init__(self, topo: ShardTopology, deg_global_dinv, hub_degree=64, chunk_edges=256, group=None, step_fn=None,
+                 alpha=0.1):
+        import ctypes as C
+        from .plan import build_stream_plan
+        self.topo, self.group, self._step_fn, self.alpha = topo, group, step_fn, float(alpha)
+        dev = topo.indices.device
+        self.on_gpu = dev.type == "cuda"
+        P, rank, n_local = topo.world, topo.rank, topo.n_local
+        if P > self.MAX_PEERS:
+            raise ValueError(f"the fused push addresses at most {self.MAX_PEERS} ranks")
+        lo = topo.bounds[rank]
+        bnd = torch.tensor(topo.bounds, dtype=torch.int64, device=dev)
+        ip = topo.indptr
+        cnt = ip[1:] - ip[:-1]
+        dinv_ext = torch.cat([deg_global_dinv[lo: lo + n_local], deg_global_dinv[topo.halo_cols]]).to(torch.float64)
+        deg_ext = torch.round(1.0 / (dinv_ext * dinv_ext)).to(torch.int64)
+        hub_ext = deg_ext >= int(hub_degree)
+        row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), cnt)
+        col = topo.indices.to(torch.int64)
+        remote = col >= n_local
+        drop = hub_ext[row_of] & remote                      # a hub's remote columns are summed where they live
+        virt = remote & hub_ext[col]                         # (remote hub h, local row c): c is a column of h's virtual row
+        # ---- new column space
+        vh_old = torch.unique(col[virt], sorted=True)        # old halo slots of the remote hubs I contribute to
+        nv = int(vh_old.numel())
+        keep = ~drop
+        halo_old = torch.unique(col[keep & remote], sorted=True)
+        nh = int(halo_old.numel())
+        self.n_virtual, self.n_halo = nv, nh
+        halo_global = topo.halo_cols[halo_old - n_local]
+        owner_h = torch.searchsorted(bnd, halo_global, right=True) - 1
+        recv_counts = torch.bincount(owner_h, minlength=P).tolist() if nh else [0] * P
+        # ---- main CSR: local rows (hub rows truncated) then virtual rows
+        kcol = col[keep]
+        kcol = torch.where(kcol < n_local, kcol, n_local + nv + torch.searchsorted(halo_old, kcol))
+        kcnt = torch.bincount(row_of[keep], minlength=n_local)
+        kval = (dinv_ext[row_of[keep]] * dinv_ext[col[keep]]).to(torch.float32)
+        v_of = torch.searchsorted(vh_old, col[virt])         # virtual row of every contributing edge
+        vperm = torch.sort(v_of * n_local + row_of[virt], stable=True).indices
+        vcol = row_of[virt][vperm]
+        vval = (dinv_ext[col[virt]] * dinv_ext[row_of[virt]]).to(torch.float32)[vperm]
+        vcnt = torch.bincount(v_of, minlength=nv)
+        n_rows = n_local + nv
+        self.n_rows = n_rows
+        mip = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+        mip[1:] = torch.cumsum(torch.cat([kcnt, vcnt]), 0)
+        mcol = torch.cat([kcol, vcol]).to(torch.int32)
+        mval = torch.cat([kval, vval])
+        oma = 1.0 - self.alpha
+        rd_y = torch.cat([deg_ext[:n_local].to(torch.float32), torch.full((nv,), oma, dtype=torch.float32, device=dev)])
+        rd_z = torch.cat([deg_ext[:n_local].to(torch.float32), torch.full((nv,), oma * oma, dtype=torch.float32, device=dev)])
+        order = torch.sort(mip[1:] - mip[:-1], descending=True, stable=True).indices
+        plan_y = build_stream_plan(mip, mcol, mval, chunk_edges, order, row_deg=rd_y)
+        import dataclasses
+        plan_z = dataclasses.replace(plan_y, row_deg=rd_z.contiguous(),
+                                     fix_deg=rd_z[plan_y.fix_row.to(torch.int64)].contiguous(), _struct=None)
+        self.main_y, self.main_z = _SubGraph(plan_y, step_fn), _SubGraph(plan_z, step_fn)
+        # ---- who contributes to whom: hub ids I add to, grouped by owner -> the owners learn their contributors
+        vh_global = topo.halo_cols[vh_old - n_local]
+        v_owner = torch.searchsorted(bnd, vh_global, right=True) - 1
+        out_counts = torch.bincount(v_owner, minlength=P) if nv else torch.zeros(P, dtype=torch.int64, device=dev)
+        in_counts = torch.empty(P, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(in_counts, out_counts, group=group)
+        ic, oc = [int(x) for x in in_counts.tolist()], [int(x) for x in out_counts.tolist()]
+        contrib = torch.empty(sum(ic), dtype=torch.int64, device=dev)      # global ids of MY hubs, grouped by contributor
+        dist.all_to_all_single(contrib, vh_global.contiguous(), output_split_sizes=ic, input_split_sizes=oc, group=group)
+        n_ps = int(contrib.numel())
+        self.n_pslots = n_ps
+        ps_base = n_local + nv + nh                                       # first partial slot of MY buffer
+        # each contributor learns where its block of slots starts in my buffer
+        offs = torch.tensor([ps_base + sum(ic[:q]) for q in range(P)], dtype=torch.int64, device=dev)
+        their = torch.empty(P, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(their, offs, group=group)                 # their[q]: start of my block in q's buffer
+        # ---- combine CSR: hub row <- its partial slots
+        crow = contrib - lo
+        if n_ps:
+            assert int(crow.min()) >= 0 and int(crow.max()) < n_local and bool(hub_ext[crow].all())
+        cslot = ps_base + torch.arange(n_ps, device=dev, dtype=torch.int64)
+        cperm = torch.sort(crow, stable=True).indices
+        ccnt = torch.bincount(crow, minlength=n_rows) if n_ps else torch.zeros(n_rows, dtype=torch.int64, device=dev)
+        cip = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+        cip[1:] = torch.cumsum(ccnt, 0)
+        combined = torch.nonzero(ccnt > 0).flatten()
+        self.combined = combined
+        self.comb_y = self.comb_z = None
+        if n_ps:
+            cplan_y = build_stream_plan(cip, cslot[cperm].to(torch.int32), None, chunk_edges, combined, subset=True, row_deg=rd_y)
+            cplan_z = dataclasses.replace(cplan_y, row_deg=rd_z.contiguous(),
+                                          fix_deg=rd_z[cplan_y.fix_row.to(torch.int64)].contiguous(), _struct=None)
+            self.comb_y, self.comb_z = _SubGraph(cplan_y, step_fn), _SubGraph(cplan_z, step_fn)
+        # ---- halo lists over the reduced halo
+        topo2 = ShardTopology(rank=rank, world=P, bounds=list(topo.bounds), n_local=n_local, indptr=mip[: n_local + 1],
+                              indices=mcol[: int(mip[n_local])], halo_cols=halo_global, recv_counts=[int(c) for c in recv_counts],
+                              interior=torch.zeros(n_local, dtype=torch.bool, device=dev))
+        self.hx = HaloExchange(topo2, group)
+        mine = torch.tensor(recv_counts + [n_local + nv, n_local + nv + nh + n_ps], dtype=torch.int64, device=dev)
+        allv = torch.empty(P * (P + 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allv, mine, group=group)
+        allv = allv.view(P, P + 2).cpu()
+        self.dst_off = [int(allv[q, P]) + int(allv[q, :rank].sum()) for q in range(P)]     # my rows in q's halo region
+        self.rows_alloc = int(allv[:, P + 1].max())
+        if self.rows_alloc >= (1 << 28):
+            raise ValueError("shard too large for the 28-bit slot field of the push code")
+        rows, codes, self.soffs, o = [], [], [], 0
+        for q in range(P):
+            self.soffs.append(o)
+            ns = self.hx.send_counts[q]
+            if ns:
+                rows.append(self.hx.send_idx[o: o + ns])
+                codes.append((q << 28) + self.dst_off[q] + torch.arange(ns, device=dev, dtype=torch.int64))
+            o += ns
+        rows = torch.cat(rows) if rows else torch.zeros(0, dtype=torch.int64, device=dev)
+        codes = torch.cat(codes) if codes else torch.zeros(0, dtype=torch.int64, device=dev)
+        is_comb = torch.zeros(n_rows, dtype=torch.bool, device=dev)
+        is_comb[combined] = True
+        late = is_comb[rows] if rows.numel() else torch.zeros(0, dtype=torch.bool, device=dev)
+        # virtual rows: one destination each, the slot the owner reserved for (me, hub)
+        vrows = n_local + torch.arange(nv, device=dev, dtype=torch.int64)
+        if nv:
+            first_of_owner = torch.cumsum(out_counts, 0) - out_counts
+            vcodes = (v_owner << 28) + their[v_owner] + (torch.arange(nv, device=dev, dtype=torch.int64) - first_of_owner[v_owner])
+        else:
+            vcodes = torch.zeros(0, dtype=torch.int64, device=dev)
+        self.push_input = _push_arrays(n_rows, rows, codes, dev)                              # halo of the caller's input
+        self.push_main = _push_arrays(n_rows, torch.cat([rows[~late], vrows]), torch.cat([codes[~late], vcodes]), dev)
+        self.push_comb = _push_arrays(n_rows, rows[late], codes[late], dev)
+        self.handles, self._bases = {}, {}
+        self._C = C
+        self.transport_name = "hybrid-push" if self.on_gpu else "hybrid-p2p"
+        self.phases, self.rounds = "hub rows summed where their columns live; two launches and two barriers per step", []
+        self.plans = [self.main_y] + ([self.comb_y] if self.comb_y is not None else [])
+        self.stats = {"n_local": n_local, "n_virtual": nv, "n_halo": nh, "n_halo_1d": topo.n_halo, "n_pslots": n_ps,
+                      "hub_rows_local": int(hub_ext[:n_local].sum()), "combined_rows": int(combined.numel())}
+
+    # buffers, barrier and the input halo are those of the 1-D fused form
+    alloc = FusedPushPropagation.alloc
+    _barrier = FusedPushPropagation._barrier
+
+    def n_ext(self):
+        return self.rows_alloc
+
+    def _push_cpu(self, buf, lst):
+        """gloo stand-in for the in-kernel peer stores of one launch: (slot, row) pairs, peer by peer."""
+        P, rank = self.topo.world, self.topo.rank
+        peer_of, slot_of = lst["codes"] >> 28, lst["codes"] & 0x0FFFFFFF
+        out_n = torch.bincount(peer_of, minlength=P) if peer_of.numel() else torch.zeros(P, dtype=torch.int64)
+        in_n = torch.empty(P, dtype=torch.int64)
+        dist.all_to_all_single(in_n, out_n, group=self.group)
+        perm = torch.sort(peer_of, stable=True).indices if peer_of.numel() else peer_of
+        F = buf.shape[1]
+        send_slots, send_rows = slot_of[perm].contiguous(), buf[lst["rows"][perm]].contiguous()
+        isz, osz = [int(x) for x in in_n.tolist()], [int(x) for x in out_n.tolist()]
+        rs = torch.empty(sum(isz), dtype=torch.int64)
+        rd = torch.empty((sum(isz), F), dtype=buf.dtype)
+        dist.all_to_all_single(rs, send_slots, output_split_sizes=isz, input_split_sizes=osz, group=self.group)
+        dist.all_to_all_single(rd, send_rows, output_split_sizes=isz, input_split_sizes=osz, group=self.group)
+        buf[rs] = rd
+
+    def _push_input(self, buf):
+        t = self.topo
+        if self.on_gpu:
+            from .ops import gather_rows
+            h, F = self.handles[buf.data_ptr()]
+            for d in range(1, t.world):
+                q = (t.rank + d) % t.world
+                ns = self.hx.send_counts[q]
+                if ns:
+                    peer = h.get_buffer(q, (self.rows_alloc, F), torch.float32)
+                    gather_rows(buf[: t.n_local], self.hx.send_idx[self.soffs[q]: self.soffs[q] + ns],
+                                peer[self.dst_off[q]: self.dst_off[q] + ns])
+            self._barrier(buf)
+        else:
+            self._push_cpu(buf, self.push_input)
+
+    def transfers_only(self, buf):
+        if self.topo.world > 1:
+            self._push_input(buf)
+
+    def _launch(self, sub, src, T, dst, alpha, epi, use_vals, lst):
+        if self._step_fn is not None:
+            self._step_fn(sub.plan, src, T, dst, alpha, epi, use_vals)
+            if lst is not None:
+                self._push_cpu(dst, lst)
+            return
+        from . import _lib
+        lib = _lib.load()
+        F = src.shape[1]
+        plan = sub.plan
+        partial = None
+        if plan.n_slots:
+            partial = sub._partial.get(F)
+            if partial is None:
+                partial = torch.empty(plan.n_slots * F, dtype=torch.float32, device=src.device)
+                sub._partial[F] = partial
+        if lst is not None:
+            rc = lib.ppnp_spmm_step_push(plan.struct(), _lib.ptr(src), _lib.ptr(T), _lib.ptr(dst), _lib.ptr(partial), F, F,
+                                         float(alpha), int(epi), int(bool(use_vals)), _lib.ptr(lst["ptr"]), _lib.ptr(lst["code"]),
+                                         _lib.ptr(lst["first"]), self._bases[dst.data_ptr()], self.topo.world, _lib.current_stream())
+        else:
+            rc = lib.ppnp_spmm_step(plan.struct(), _lib.ptr(src), _lib.ptr(T), _lib.ptr(dst), _lib.ptr(partial), F, F,
+                                    float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
+        _lib.check(rc, "ppnp_spmm_step_push")
+
+    def propagate(self, H_ext, Z_ext, S_ext, K, alpha):
+        """H_ext rows past n_local must be zero on entry apart from what this call ships (the teleport rows of
+        the virtual rows are read as zeros)."""
+        from . import _lib
+        if K < 2:
+            raise NotImplementedError("the hybrid form runs the value-free iteration (K >= 2)")
+        if abs(float(alpha) - self.alpha) > 1e-12:
+            raise ValueError("alpha is baked into the virtual rows' epilogue: build the object with the alpha you propagate with")
+        t = self.topo
+        multi = t.world > 1
+        if multi:
+            self._push_input(H_ext)
+        src = H_ext
+        for k in range(1, K + 1):
+            dst = Z_ext if (K - k) % 2 == 0 else S_ext
+            if k == 1:
+                epi, use_vals, main, comb = _lib.EPI_Z2Y, True, self.main_z, self.comb_z
+            elif k == K:
+                epi, use_vals, main, comb = _lib.EPI_Y2Z, False, self.main_z, self.comb_z
+            else:
+                epi, use_vals, main, comb = _lib.EPI_Y, False, self.main_y, self.comb_y
+            self._launch(main, src, H_ext, dst, alpha, epi, use_vals, self.push_main if multi else None)
+            if multi:
+                self._barrier(dst)                       # every partial row has landed
+                if comb is not None:
+                    last = k == K
+                    self._launch(comb, dst, dst, dst, alpha, epi | _lib.EPI_ACC | _lib.EPI_INPLACE, False,
+                                 None if last else self.push_comb)
+                if k < K:
+                    self._barrier(dst)                   # every finished hub row has landed
+            src = dst
+        return Z_ext[: t.n_local]
+
+
+_PUSH_CLASSES = (PipelinedPushPropagation, FusedPushPropagation, HybridPushPropagation)
+
+
 class _SubGraph:
     def __init__(self, plan, step_fn=None):
         self.plan, self._step_fn = plan, step_fn
@@ -1013,7 +1294,7 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
 
 
 def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4,
-                      carve=None):
+                      carve=None, hub_degree=64):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
@@ -1036,14 +1317,16 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
             import warnings
             warnings.warn(f"peer-memory transport unavailable ({type(e).__name__}: {e}); falling back to NCCL point-to-point")
             prop = PartitionedPropagation(topo, dinv, phases="one", transport="p2p")
+    elif transport == "hybrid" and world > 1:
+        prop = HybridPushPropagation(topo, dinv, hub_degree=hub_degree, alpha=alpha)
     elif transport == "pipe" and world > 1:
         prop = PipelinedPushPropagation(topo, dinv, row_groups=row_groups)
     else:
-        prop = PartitionedPropagation(topo, dinv, phases=phases, transport=("p2p" if transport in ("pipe", "fused") else transport))
+        prop = PartitionedPropagation(topo, dinv, phases=phases, transport=("p2p" if transport in ("pipe", "fused", "hybrid") else transport))
     del dinv
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
-    H, G, Z, S = (prop.alloc(F, 4) if isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation)) else prop.transport.alloc(F, 4))
+    H, G, Z, S = (prop.alloc(F, 4) if isinstance(prop, _PUSH_CLASSES) else prop.transport.alloc(F, 4))
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     for b in (H, G, Z, S):
         b.zero_()
@@ -1108,7 +1391,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     from . import _lib as _l
 
     def transfers_only():
-        if isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation)):
+        if isinstance(prop, _PUSH_CLASSES):
             if world > 1:
                 prop.transfers_only(Z)
             return
@@ -1121,7 +1404,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         first = True
         for p in prop.plans:
             if p is not None:
-                acc_pass = (not first) and not isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation))
+                acc_pass = (not first) and not isinstance(prop, _PUSH_CLASSES)
                 p.step(Z, S if acc_pass else H, S, alpha, _l.EPI_Y | (_l.EPI_ACC if acc_pass else 0), False)
             first = False
     ms_compute = timed(compute_only)
@@ -1134,7 +1417,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         transfers_only()
     b_.record(); torch.cuda.synchronize()
     my_xfer_us = int(a_.elapsed_time(b_) / 4 * 1e3)
-    hx = prop.hx if isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation)) else getattr(prop.transport, "hx", None)
+    hx = prop.hx if isinstance(prop, _PUSH_CLASSES) else getattr(prop.transport, "hx", None)
     sent_rows = sum(hx.send_counts) if hx is not None else 0
     stats = torch.tensor([int(indptr[-1]), topo.n_halo, topo.n_local, int(topo.interior.sum()), sent_rows, my_xfer_us], dtype=torch.int64, device=dev)
     allstats = [torch.empty_like(stats) for _ in range(world)]
@@ -1145,7 +1428,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         if p is not None:
             launches += 2 if p.plan.n_fix > 0 else 1
     launches += (world - 1) if prop.transport_name in ("pull", "push") else 0
-    if isinstance(prop, (PipelinedPushPropagation, FusedPushPropagation)):
+    if isinstance(prop, _PUSH_CLASSES):
         launches += (world - 1) * getattr(prop, "G", 0)
     work = 2 * K * nnz * F
     return {

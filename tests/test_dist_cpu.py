@@ -76,13 +76,27 @@ def worker(rank, world, port, phases, outdir):
             prop = pd.FusedPushPropagation(topo, dinv, chunk_edges=128, step_fn=walker_step,
                                            carve=dict(block_cols=100, n_blocks=6, min_piece=3))
             assert prop.sub.plan.carve["carved_edges"] > 0 and not prop.sub.plan.wide_cta
+        elif phases.startswith("hybrid"):  # hub rows summed where their columns live (partial rows + combine launch)
+            prop = pd.HybridPushPropagation(topo, dinv, hub_degree=int(phases[6:]), chunk_edges=128, step_fn=walker_step,
+                                            alpha=alpha)
+            st = prop.stats
+            assert st["n_halo"] <= st["n_halo_1d"]
+            tot = torch.tensor([st["n_virtual"], st["n_pslots"], st["combined_rows"], st["n_halo_1d"] - st["n_halo"]])
+            dist.all_reduce(tot)
+            assert int(tot[0]) == int(tot[1])                              # every virtual row has exactly one slot somewhere
+            if int(phases[6:]) <= 64:
+                assert int(tot[0]) > 0 and int(tot[2]) > 0
+            else:                                                           # no row is a hub: the plain 1-D form
+                assert int(tot[0]) == 0 and int(tot[2]) == 0 and int(tot[3]) == 0
+            if int(phases[6:]) <= 16:
+                assert int(tot[3]) > 0                                      # the halo really shrinks
         elif phases.startswith("pipe"):
             prop = pd.PipelinedPushPropagation(topo, dinv, chunk_edges=128, row_groups=int(phases[4:]), step_fn=walker_step)
         else:
             prop = pd.PartitionedPropagation(topo, dinv, chunk_edges=128, phases=phases, step_fn=walker_step)
         rng = np.random.RandomState(0)
         Hg = rng.randn(n, F).astype(np.float32)                                # the same global H on every rank
-        n_ext = prop.rows_alloc if (phases.startswith("pipe") or phases.startswith("fused")) else prop.n_ext()
+        n_ext = prop.rows_alloc if (phases.startswith("pipe") or phases.startswith("fused") or phases.startswith("hybrid")) else prop.n_ext()
         H = torch.zeros(n_ext, F); H[: topo.n_local] = torch.from_numpy(Hg[lo:hi])
         Z, S = torch.zeros_like(H), torch.zeros_like(H)
         out = prop.propagate(H, Z, S, K, alpha)
@@ -91,9 +105,16 @@ def worker(rank, world, port, phases, outdir):
         ref = oracle.appnp(A, Hg.astype(np.float64), alpha, K)[lo:hi]
         err = relerr(out.numpy(), ref)
         assert err < 1e-5, err
-        # K = 1 path (plain epilogue)
-        out1 = prop.propagate(H, Z, S, 1, alpha)
-        assert relerr(out1.numpy(), oracle.appnp(A, Hg.astype(np.float64), alpha, 1)[lo:hi]) < 1e-5
+        if phases.startswith("hybrid"):
+            # a second call on the same buffers (stale partial rows from the first one must not matter), K = 2
+            out2 = prop.propagate(H, Z, S, 2, alpha)
+            assert relerr(out2.numpy(), oracle.appnp(A, Hg.astype(np.float64), alpha, 2)[lo:hi]) < 1e-5
+            with pytest.raises(NotImplementedError):
+                prop.propagate(H, Z, S, 1, alpha)
+        else:
+            # K = 1 path (plain epilogue)
+            out1 = prop.propagate(H, Z, S, 1, alpha)
+            assert relerr(out1.numpy(), oracle.appnp(A, Hg.astype(np.float64), alpha, 1)[lo:hi]) < 1e-5
         with open(os.path.join(outdir, f"ok_{rank}"), "w") as f:
             f.write(f"{err}\n")
     finally:
@@ -101,7 +122,8 @@ def worker(rank, world, port, phases, outdir):
 
 
 @pytest.mark.parametrize("world,phases", [(2, "peer"), (2, "one"), (3, "peer"), (3, "two"), (2, "pipe3"), (3, "pipe4"), (3, "pipe1"), (2, "fused"), (3, "fused"),
-                                          (2, "fused-carve"), (3, "fused-carve")])
+                                          (2, "fused-carve"), (3, "fused-carve"),
+                                          (2, "hybrid8"), (3, "hybrid40"), (2, "hybrid100000")])
 def test_partitioned_propagation_gloo(tmp_path, world, phases):
     port = 29600 + world * 10 + len(phases) + (os.getpid() % 50)
     mp.spawn(worker, args=(world, port, phases, str(tmp_path)), nprocs=world, join=True)

@@ -17,3 +17,6 @@ for v in carve512x64+idx16 carve512x64T8+idx16+interleave; do
       -o gpurun_out/r02_prof_${v//+/_} -f python tools/bench_variants.py $v > gpurun_out/r02_ncu_${v//+/_}.log 2>&1
 done
 ls -la gpurun_out | tail -8
+# multi-GPU (run with gpurun --gpus 2 / 8): the hybrid exchange and the L2-carved shard streams against the fused default
+#   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus N --steps 3 --warmup 2 [--transport hybrid --hub-degree 64 | --order carve --carve-block-cols 6000000 --carve-blocks 16 --carve-min-piece 16]
+#   pytest tests/test_gpu_dist.py -m gpu   (2 GPUs)
