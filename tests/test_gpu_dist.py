@@ -28,6 +28,10 @@ def worker(rank, world, port, mode, outdir):
         phases, transport = mode.split("/")
         if transport == "fused":
             prop = pd.FusedPushPropagation(topo, dinv)
+        elif transport == "fusedcarve":        # L2-sized hot column blocks of the shard first (not yet run on GPUs)
+            prop = pd.FusedPushPropagation(topo, dinv, carve=dict(block_cols=16384, n_blocks=8, min_piece=8))
+        elif transport == "hybrid":            # hub rows summed where their columns live (not yet run on GPUs)
+            prop = pd.HybridPushPropagation(topo, dinv, hub_degree=int(phases), alpha=alpha)
         elif transport == "pipe":
             prop = pd.PipelinedPushPropagation(topo, dinv, row_groups=int(phases))
         else:
@@ -38,7 +42,7 @@ def worker(rank, world, port, mode, outdir):
         old_of_new = np.argsort(new_of_old)
         mine = old_of_new[lo:hi]
         Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
-        H, Z, S = prop.alloc(F, 3) if transport in ("pipe", "fused") else prop.transport.alloc(F, 3)
+        H, Z, S = prop.alloc(F, 3) if transport in ("pipe", "fused", "fusedcarve", "hybrid") else prop.transport.alloc(F, 3)
         H.zero_()
         H[: topo.n_local] = torch.from_numpy(Hg[mine]).to(dev)
         out = prop.propagate(H, Z, S, K, alpha).cpu().numpy()
@@ -55,7 +59,8 @@ def worker(rank, world, port, mode, outdir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["x/fused", "4/pipe", "1/pipe", "two/push", "one/push", "peer/pull", "peer/p2p", "one/p2p"])
+@pytest.mark.parametrize("mode", ["x/fused", "4/pipe", "1/pipe", "two/push", "one/push", "peer/pull", "peer/p2p", "one/p2p",
+                                  "x/fusedcarve", "64/hybrid", "512/hybrid"])
 def test_partitioned_matches_oracle_on_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
