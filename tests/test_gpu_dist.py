@@ -64,6 +64,9 @@ def worker(rank, world, port, mode, outdir):
 def test_partitioned_matches_oracle_on_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    if mode.split("/")[1] in ("fusedcarve", "hybrid") and os.environ.get("PPNP_TEST_UNVALIDATED") != "1":
+        pytest.skip("written after the round's GPU budget was spent; parity-green under gloo only -- set "
+                    "PPNP_TEST_UNVALIDATED=1 to run it on GPUs (tools/gpu_calls/r02_first_call.sh does)")
     port = 29700 + len(mode) + (hash(mode) % 40) + (os.getpid() % 50)
     mp.spawn(worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"ok_{r}") for r in range(2))

@@ -19,4 +19,4 @@ done
 ls -la gpurun_out | tail -8
 # multi-GPU (run with gpurun --gpus 2 / 8): the hybrid exchange and the L2-carved shard streams against the fused default
 #   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus N --steps 3 --warmup 2 [--transport hybrid --hub-degree 64 | --order carve --carve-block-cols 6000000 --carve-blocks 16 --carve-min-piece 16]
-#   pytest tests/test_gpu_dist.py -m gpu   (2 GPUs)
+#   PPNP_TEST_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -q   (2 GPUs)
