@@ -529,3 +529,117 @@ def graph_standardize(indptr, indices, make_unweighted=True, make_undirected=Tru
     if nnz_out < (1 << 31):
         ip = ip.to(torch.int32)
     return ip, out_indices[:nnz_out], out_keep[:n_keep].to(torch.int64)
+
+
+# ------------------------------------------------------------------------------ sparse-input first layer
+class SparseInput:
+    """The attribute matrix X (n x F_in, ~2 % dense; main.py:90-92 densifies it) kept sparse for the
+    encoder's first layer (model.py:47-48: Dropout then CustomLinear), SURVEY.md section 8f rank 3.
+
+    ``dropout(X) @ W`` is an SpMM whose "adjacency" is X's CSR and whose feature matrix is W (F_in x hidden):
+    the propagation kernel runs it as it is (stored-value form, alpha = 0, accumulate epilogue onto a zeroed
+    output).  The gradient ``dropout(X)^T @ dOut`` is the same kernel over the stream of X^T.  Dropout is
+    applied to the stored values of the stream (one Bernoulli draw per stored entry, scaled by 1/(1-p));
+    the dense n x F_in mask of nn.Dropout never exists.  Two stream plans are built once; rows (or
+    columns) without entries are simply absent from their stream and stay zero."""
+
+    def __init__(self, indptr, indices, values, n_cols, chunk_edges=256):
+        dev = indices.device            # index bookkeeping runs wherever the arrays live; the launches need CUDA
+        ip = indptr.to(torch.int64)
+        self.n_rows, self.n_cols = int(ip.numel()) - 1, int(n_cols)
+        idx = indices.to(torch.int64)
+        nnz = int(idx.numel())
+        self.nnz = nnz
+        self.values = values.to(torch.float32).contiguous()
+        cnt = ip[1:] - ip[:-1]
+        row_of = torch.repeat_interleave(torch.arange(self.n_rows, device=dev), cnt)
+        # X^T as CSR: entries sorted by (column, row)
+        tperm = torch.sort(idx * self.n_rows + row_of, stable=True).indices
+        tcnt = torch.bincount(idx, minlength=self.n_cols)
+        tip = torch.zeros(self.n_cols + 1, dtype=torch.int64, device=dev)
+        tip[1:] = torch.cumsum(tcnt, 0)
+        self.fwd, self.fwd_edge = self._stream(ip, idx.to(torch.int32), cnt, chunk_edges, None)
+        self.bwd, self.bwd_edge = self._stream(tip, row_of[tperm].to(torch.int32), tcnt, chunk_edges, tperm)
+
+    @staticmethod
+    def _stream(ip, cols, cnt, chunk_edges, edge_of_csr):
+        """Stream plan over the non-empty rows (degree order) + the original entry behind every stream position."""
+        dev = cols.device
+        rows = torch.nonzero(cnt > 0).flatten()
+        order = rows[torch.sort(cnt[rows], descending=True, stable=True).indices]
+        if order.numel() == 0:
+            return None, None
+        plan = build_stream_plan(ip, cols, torch.ones(cols.numel(), dtype=torch.float32, device=dev), chunk_edges, order, subset=True)
+        L = cnt[order]
+        a = torch.cumsum(L, 0) - L
+        src = torch.repeat_interleave(ip[:-1][order] - a, L) + torch.arange(int(L.sum()), device=dev, dtype=torch.int64)
+        if edge_of_csr is not None:
+            src = edge_of_csr[src]
+        return plan, src
+
+    @classmethod
+    def from_dense(cls, X, chunk_edges=256):
+        """From the dense tensor main.py:91-92 builds (torch's dense -> CSR conversion is plumbing)."""
+        s = X.to_sparse_csr()
+        return cls(s.crow_indices(), s.col_indices(), s.values(), X.shape[1], chunk_edges)
+
+    def _with_values(self, plan, edge_of_pos, scale_per_entry):
+        import dataclasses
+        v = self.values if scale_per_entry is None else self.values * scale_per_entry
+        vals = torch.zeros(plan.cols.numel(), dtype=torch.float32, device=v.device)
+        vals[: edge_of_pos.numel()] = v[edge_of_pos]
+        return dataclasses.replace(plan, vals=vals, _struct=None)
+
+    def _run(self, plan, Zin, out):
+        lib = _lib.load()
+        _require_cuda(Zin, plan.cols)
+        F = Zin.shape[1]
+        partial = None
+        if plan.n_slots:
+            partial = torch.empty(plan.n_slots * F, dtype=torch.float32, device=Zin.device)
+        with torch.cuda.device(Zin.device):
+            rc = lib.ppnp_spmm_step(plan.struct(), _lib.ptr(Zin), _lib.ptr(out), _lib.ptr(out), _lib.ptr(partial), F, F,
+                                    0.0, _lib.EPI_PLAIN | _lib.EPI_ACC, 1, _lib.current_stream())
+        _lib.check(rc, "ppnp_spmm_step")
+        return out
+
+    def matmul(self, W, scale_per_entry=None):
+        """(X * scale) @ W  ->  [n_rows, hidden]."""
+        W = W.contiguous()
+        out = torch.zeros((self.n_rows, W.shape[1]), dtype=torch.float32, device=W.device)
+        if self.fwd is None:
+            return out
+        return self._run(self._with_values(self.fwd, self.fwd_edge, scale_per_entry), W, out)
+
+    def rmatmul(self, G, scale_per_entry=None):
+        """(X * scale)^T @ G  ->  [n_cols, hidden]."""
+        G = G.contiguous()
+        out = torch.zeros((self.n_cols, G.shape[1]), dtype=torch.float32, device=G.device)
+        if self.bwd is None:
+            return out
+        return self._run(self._with_values(self.bwd, self.bwd_edge, scale_per_entry), G, out)
+
+
+class _SparseLinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, W, sx, scale):
+        ctx.sx, ctx.scale = sx, scale
+        return sx.matmul(W, scale)
+
+    @staticmethod
+    def backward(ctx, G):
+        return ctx.sx.rmatmul(G, ctx.scale), None, None
+
+
+def sparse_first_layer(sx: SparseInput, W, p=0.5, training=True, generator=None):
+    """model.py:47-48 ``CustomLinear(Dropout(p)(X))`` (bias-free part) with X kept sparse: differentiable w.r.t. W."""
+    if W.dtype != torch.float32 or W.dim() != 2 or W.shape[0] != sx.n_cols:
+        raise ValueError(f"W must be a float32 [{sx.n_cols}, hidden] matrix")
+    scale = None
+    if training and p > 0.0:
+        if p >= 1.0:
+            scale = torch.zeros(sx.nnz, dtype=torch.float32, device=W.device)
+        else:
+            keep = torch.empty(sx.nnz, dtype=torch.float32, device=W.device).bernoulli_(1.0 - p, generator=generator)
+            scale = keep / (1.0 - p)
+    return _SparseLinearFunction.apply(W, sx, scale)

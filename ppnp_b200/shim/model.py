@@ -146,6 +146,10 @@ class PPNP(nn.Module):
         self._graph = None
         self._alpha = None
         self._ppr_bf16 = None
+        # PPNP_SPARSE_X=1: the first encoder layer reads X as a sparse matrix (ppnp_b200.SparseInput) in the
+        # full-batch branch (model.py:63); main.py still hands over the dense tensor, its CSR is built once
+        self._sparse_x = os.environ.get("PPNP_SPARSE_X", "0") == "1"
+        self._sx, self._sx_key = None, None
         if self.mode == "appnp":
             import helpers as _h            # the shim module that recorded the graph (helpers.compute_ppr)
             if _h.LAST_GRAPH["ahat"] is None:
@@ -167,9 +171,23 @@ class PPNP(nn.Module):
             return _GemmBf16.apply(H, shadow, ppr.as_subclass(torch.Tensor), idx)
         return _P.ppr_matmul(ppr.as_subclass(torch.Tensor), H, idx)
 
+    def _encode_full(self, X):
+        """model.py:46-52 on the whole attribute matrix; with PPNP_SPARSE_X=1 the Dropout + CustomLinear pair
+        (model.py:47-48) runs over X's stored entries only."""
+        if not (self._sparse_x and X.is_cuda and X.dim() == 2):
+            return self.encoder(X)
+        key = (X.data_ptr(), tuple(X.shape), X._version)
+        if self._sx_key != key:
+            self._sx, self._sx_key = _P.SparseInput.from_dense(X), key
+        drop, lin = self.encoder[0], self.encoder[1]
+        h = _P.sparse_first_layer(self._sx, lin.weight, drop.p, self.training)
+        if lin.bias is not None:
+            h = h + lin.bias
+        return self.encoder[4](self.encoder[3](self.encoder[2](h)))
+
     def forward(self, X, idx=None, ppr=None):
         if idx is not None:
-            H = self.encoder(X)
+            H = self._encode_full(X)
             if self.mode == "appnp":
                 return _P.appnp(H, self._graph, self.K, self._alpha)[idx]
             return self._apply_ppr(self.ppr, H, idx)
