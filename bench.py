@@ -14,8 +14,9 @@ Workloads (BASELINE.json configs):
   rmat100m (N>1 default)  config 5: R-MAT n=100 000 000, ~2 B non-zeros, F=16, rows partitioned
                           over the N GPUs, halo exchange over NCCL each iteration (strong scaling)
   tiny                    a 20 k-node graph for plumbing checks
-The processing order of the edge stream is picked by measurement before the warm-up (--order auto:
-degree order or an L2-blocked carved order, same results either way; config.order names the one used).
+--order auto picks the processing order of the edge stream by measurement before the warm-up (degree
+order or an L2-blocked carved order, same results either way; config.order names the one used); the
+default is the measured degree order.
 One JSON line on stdout (rank 0).  `value` = device-resident throughput; `e2e` = the same pass
 through the public API with pinned HOST buffers, H2D/D2H copies inside the timed region.
 """
@@ -475,8 +476,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--order", default="auto", choices=["auto", "natural", "degree", "carve"],
-                    help="processing order of the edge stream; auto (default) times degree order and two L2-blocked carves and keeps the fastest")
+    ap.add_argument("--order", default="degree", choices=["auto", "natural", "degree", "carve"],
+                    help="processing order of the edge stream; auto times degree order and two L2-blocked carves and keeps the fastest")
     ap.add_argument("--idx16", dest="idx16", action="store_true", default=True,
                     help="16-byte staging of a lane-transposed index stream (default; bit-identical results)")
     ap.add_argument("--no-idx16", dest="idx16", action="store_false", help="4-byte staging of the linear index stream")
