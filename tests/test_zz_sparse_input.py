@@ -79,3 +79,40 @@ def test_sparse_first_layer_matches_dense_torch(name):
     gref = Xd.double().T @ G.double()
     assert float((W.grad.double() - gref).norm() / gref.norm()) < 1e-6
     assert 0.45 < float(keep.mean()) < 0.55
+
+
+@pytest.mark.gpu
+def test_shim_sparse_x_switch_matches_the_dense_encoder(monkeypatch):
+    """PPNP_SPARSE_X=1: model.PPNP.forward(X, idx) (model.py:61-63) with the first layer over X's stored
+    entries equals the dense encoder in eval mode, and trains (the weight gradient flows) in train mode."""
+    import os
+    import sys
+    from util import ROOT
+    monkeypatch.setenv("PPNP_SPARSE_X", "1")
+    monkeypatch.syspath_prepend(os.path.join(ROOT, "ppnp_b200", "shim"))
+    for m in ("helpers", "model"):
+        sys.modules.pop(m, None)
+    import model
+    z, _ = load_std("citeseer")
+    dev = torch.device("cuda:0")
+    n, F_in = int(z["attr_shape"][0]), int(z["attr_shape"][1])
+    X = torch.sparse_csr_tensor(torch.from_numpy(z["attr_indptr"].astype(np.int64)), torch.from_numpy(z["attr_indices"].astype(np.int64)),
+                                torch.from_numpy(z["attr_data"]), size=(n, F_in)).to_dense().to(dev)
+    torch.manual_seed(0)
+    ppr = torch.rand(n, n) * (torch.rand(n, n) < 0.01)
+    net = model.PPNP(F_in, torch.tensor(6), ppr).to(dev)
+    idx = torch.arange(0, n, 7, device=dev)
+    net.eval()
+    with torch.no_grad():
+        a = net(X, idx)
+        net._sparse_x = False
+        b = net(X, idx)
+        net._sparse_x = True
+    assert float((a - b).norm() / b.norm()) < 1e-5
+    net.train()
+    out = net(X, idx)
+    out.sum().backward()
+    g = net.encoder[1].weight.grad
+    assert g is not None and float(g.abs().sum()) > 0 and torch.isfinite(g).all()
+    for m in ("helpers", "model"):
+        sys.modules.pop(m, None)
