@@ -1,0 +1,24 @@
+"""File -> GPU standardise -> GPU calc_A_hat (ppnp_b200/io.py standardized_graph) against the reference's
+main.py:73-75 + helpers.py:58-66 pipeline.  Composed of ops that are parity-green on the GPU; the composition
+itself was written after the round's GPU budget was spent (the file sorts last)."""
+import numpy as np
+import pytest
+
+from util import load_golden
+from test_io import CASES, write_flat_dict
+from ppnp_b200 import io as pio
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cora_ml", "citeseer"])
+def test_file_to_normalised_graph_matches_reference_pipeline(tmp_path, name):
+    """npz file -> GPU standardise -> GPU calc_A_hat == the reference's main.py:73-75 + helpers.py:58-66."""
+    p = str(tmp_path / "g.npz")
+    write_flat_dict(p, name)
+    ahat, keep, raw = pio.standardized_graph(p, device="cuda:0")
+    g = load_golden(name)
+    assert np.array_equal(ahat.indptr.cpu().numpy(), g["ahat_sym_indptr"])
+    assert np.array_equal(ahat.indices.cpu().numpy(), g["ahat_sym_indices"])
+    assert np.array_equal(ahat.val32.cpu().numpy(), g["ahat_sym_data"].astype(np.float32))
+    assert np.array_equal(keep.cpu().numpy(), CASES[f"{name}.keep"])
+    assert raw.labels[keep].numel() == ahat.n
