@@ -17,6 +17,8 @@ for v in carve512x64+idx16 carve512x64T8+idx16+interleave; do
   timeout 150 ncu --set full --clock-control none --import-source on -k regex:spmm_stream_kernel --launch-skip 3 --launch-count 1 \
       -o gpurun_out/r02_prof_${v//+/_} -f python tools/bench_variants.py $v > gpurun_out/r02_ncu_${v//+/_}.log 2>&1
 done
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r02_ncu_launches.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:spmm_stream_kernel --launch-skip 3 --launch-count 1 -o gpurun_out/r02_prof_default -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r02_ncu_default.log 2>&1
 ls -la gpurun_out | tail -8
 # multi-GPU (run with gpurun --gpus 2 / 8): the hybrid exchange and the L2-carved shard streams against the fused default
 #   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus N --steps 3 --warmup 2 [--transport hybrid --hub-degree 64 | --order carve --carve-block-cols 6000000 --carve-blocks 16 --carve-min-piece 16]
