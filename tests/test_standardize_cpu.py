@@ -49,3 +49,49 @@ def test_standardize_is_idempotent_and_rejects_unsupported():
         oracle.standardize(ip, idx, data, make_unweighted=False)
     with pytest.raises(ValueError):
         oracle.standardize(ip, idx, np.zeros_like(data))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def test_oracle_standardize_matches_reference_on_random_graphs():
+    """Beyond the frozen cases: 40 random graphs (directed, weighted, loops, several components, isolated
+    nodes, every flag combination the unit-weight pipeline has) through the reference itself."""
+    import sys
+    import warnings
+    import scipy.sparse as sp
+    sys.path.insert(0, "/root/reference")
+    try:
+        from ppnp.data.sparsegraph import SparseGraph
+    finally:
+        sys.path.remove("/root/reference")
+    rng = np.random.RandomState(11)
+    for trial in range(40):
+        n = int(rng.randint(2, 120))
+        m = int(rng.randint(0, 4 * n))
+        blocks = int(rng.randint(1, 5))
+        size = max(1, n // blocks)
+        b = rng.randint(0, blocks, m)
+        r = np.minimum(b * size + rng.randint(0, size, m), n - 1)
+        c = np.minimum(b * size + rng.randint(0, size, m), n - 1)
+        a = sp.csr_matrix((np.ones(m, dtype=np.float32), (r, c)), shape=(n, n))
+        a.sum_duplicates()
+        a.data[:] = 1.0
+        a.sort_indices()
+        flags = dict(make_unweighted=True, make_undirected=bool(rng.rand() < 0.8), no_self_loops=bool(rng.rand() < 0.8),
+                     select_lcc=bool(rng.rand() < 0.8))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            g = SparseGraph(adj_matrix=a.copy(), node_names=np.arange(n)).standardize(**flags)
+        ref = g.adj_matrix.tocsr()
+        ref.sort_indices()
+        sizes_tie = False
+        if flags["select_lcc"]:
+            # the reference's choice between equally large components is np.argsort's (unstable above 16 elements):
+            # compare only when the largest component is unique
+            comp = sp.csgraph.connected_components(a + a.T if True else a)[1]
+            cnt = np.bincount(comp)
+            sizes_tie = (cnt == cnt.max()).sum() > 1
+        if sizes_tie:
+            continue
+        ip, idx, keep = oracle.standardize(a.indptr, a.indices, a.data, **flags)
+        assert np.array_equal(ip, ref.indptr) and np.array_equal(idx, ref.indices), (trial, flags)
+        assert np.array_equal(keep, np.asarray(g.node_names)), (trial, flags)
