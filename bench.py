@@ -255,7 +255,7 @@ def run_ours(args):
         from ppnp_b200 import dist as pd
         result = pd.bench_partitioned(wl, n, raw, scale, F, KSTEPS, ALPHA, steps, warmup, dev, rank, world,
                                        phases=args.phases, transport=args.transport, stripes=args.stripes,
-                                       row_groups=args.row_groups, hub_degree=args.hub_degree,
+                                       row_groups=args.row_groups, hub_degree=args.hub_degree, idx16=args.dist_idx16,
                                        carve=({"block_cols": args.carve_block_cols, "n_blocks": args.carve_blocks,
                                                "min_piece": args.carve_min_piece} if args.order == "carve" else None))
         if rank == 0:
@@ -493,6 +493,7 @@ def main():
     ap.add_argument("--phases", default="one", choices=["peer", "two", "one"], help="multi-GPU: how a step is split")
     ap.add_argument("--row-groups", type=int, default=4, help="multi-GPU: kernels per step of the pipelined push")
     ap.add_argument("--stripes", type=int, default=0, help="multi-GPU: block-cyclic stripes per rank (0 = auto, ~4096-id stripes; 1 = plain contiguous blocks)")
+    ap.add_argument("--dist-idx16", action="store_true", help="multi-GPU fused transport: 16-byte index staging (validated on one GPU only)")
     ap.add_argument("--hub-degree", type=int, default=64, help="multi-GPU --transport hybrid: rows of at least this degree are summed where their columns live")
     ap.add_argument("--transport", default="auto", choices=["auto", "fused", "hybrid", "pipe", "pull", "push", "p2p"], help="multi-GPU: halo transport")
     args = ap.parse_args()

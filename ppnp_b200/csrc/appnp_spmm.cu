@@ -623,10 +623,11 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
     constexpr bool HAS_VARIANTS = (VEC == 4) && (G == 4 || G == 16);
     bool launched = false;
     if constexpr (HAS_VARIANTS) {
-        if ((wide || lane_group != 0) && full_tile && pa.ptr == nullptr) {
-#define PPNP_LAUNCH3(HV_, NT_, I16_)                                                                               \
+        // with a halo push only the 256-thread lane-transposed form exists (the multi-GPU shards are not carved for L1)
+        if ((wide || lane_group != 0) && full_tile && (pa.ptr == nullptr || (lane_group != 0 && !wide))) {
+#define PPNP_LAUNCH3(HV_, NT_, I16_, PU_)                                                                          \
     do {                                                                                                           \
-        auto k = spmm_stream_kernel<VEC, G, HV_, U, true, false, NT_, I16_>;                                       \
+        auto k = spmm_stream_kernel<VEC, G, HV_, U, true, PU_, NT_, I16_>;                                         \
         static thread_local int occ = 0;                                                                           \
         const int smem_bytes = (I16_ ? Stage16Cfg<G>::words_per_thread(HV_) : StageCfg<G>::words_per_thread(HV_)) * NT_ * 4; \
         if (!occ) {                                                                                                \
@@ -642,21 +643,23 @@ int launch_step(const ppnp_plan_t* p, const float* Zin, const float* T, float* Z
         k<<<grid, NT_, smem_bytes, stream>>>(p->cols, HV_ ? p->vals : nullptr, p->seg_row, p->chunk_seg, p->n_chunks,  \
                                        p->chunk_edges, Zin, T, Zout, partial, (int)ld, F, alpha, epi, p->row_deg, pa); \
     } while (0)
-            if (use_vals) {
-                if (wide && lane_group) PPNP_LAUNCH3(true, 1024, true);
-                else if (wide) PPNP_LAUNCH3(true, 1024, false);
-                else PPNP_LAUNCH3(true, 256, true);
+            if (pa.ptr != nullptr) {
+                if (use_vals) PPNP_LAUNCH3(true, 256, true, true); else PPNP_LAUNCH3(false, 256, true, true);
+            } else if (use_vals) {
+                if (wide && lane_group) PPNP_LAUNCH3(true, 1024, true, false);
+                else if (wide) PPNP_LAUNCH3(true, 1024, false, false);
+                else PPNP_LAUNCH3(true, 256, true, false);
             } else {
-                if (wide && lane_group) PPNP_LAUNCH3(false, 1024, true);
-                else if (wide) PPNP_LAUNCH3(false, 1024, false);
-                else PPNP_LAUNCH3(false, 256, true);
+                if (wide && lane_group) PPNP_LAUNCH3(false, 1024, true, false);
+                else if (wide) PPNP_LAUNCH3(false, 1024, false, false);
+                else PPNP_LAUNCH3(false, 256, true, false);
             }
 #undef PPNP_LAUNCH3
             launched = true;
         }
     }
     if (!launched && lane_group != 0) {
-        set_error("lane-transposed plans run only with F = 16 or 64 (whole tiles, 16-byte aligned) and without a halo push");
+        set_error("lane-transposed plans run only with F = 16 or 64 (whole tiles, 16-byte aligned; with a halo push: 256-thread CTAs)");
         return PPNP_ENOTSUP;
     }
     if (!launched) {

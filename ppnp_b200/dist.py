@@ -687,10 +687,12 @@ class FusedPushPropagation:
 
     MAX_PEERS = 8
 
-    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, group=None, step_fn=None, carve=None):
+    def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, group=None, step_fn=None, carve=None,
+                 idx16=False):
         """carve: keyword arguments of plan.build_carved_plan (block_cols, n_blocks, min_piece): stream the
         shard with its hot column blocks first (blocks sized for the L2: the cold gathers of the hub rows
-        stay inside an L2-resident window) instead of in plain degree order."""
+        stay inside an L2-resident window) instead of in plain degree order.
+        idx16: 16-byte staging of a lane-transposed copy of the stream (feature widths 16 and 64), as on one GPU."""
         import ctypes as C
         from .plan import build_carved_plan, build_stream_plan
         self.topo, self.group, self._step_fn = topo, group, step_fn
@@ -714,6 +716,7 @@ class FusedPushPropagation:
             plan = build_stream_plan(ip, topo.indices, vals, chunk_edges, order)
         self.sub = _SubGraph(plan, step_fn)
         self.plans = [self.sub]
+        self.idx16, self._plans16 = bool(idx16) and step_fn is None, {}
         del vals
         # push lists: for every local row, the (peer, slot) pairs that want it
         self.hx = HaloExchange(topo, group)
@@ -845,6 +848,12 @@ class FusedPushPropagation:
         lib = _lib.load()
         F = src.shape[1]
         plan = self.sub.plan
+        if self.idx16 and F in (16, 64):
+            from .plan import lane_group_for, lane_transpose
+            G = lane_group_for(F)
+            if G not in self._plans16:
+                self._plans16[G] = lane_transpose(plan, G)
+            plan = self._plans16[G]
         partial = None
         if plan.n_slots:
             partial = self.sub._partial.get(F)
@@ -1294,7 +1303,7 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
 
 
 def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4,
-                      carve=None, hub_degree=64):
+                      carve=None, hub_degree=64, idx16=False):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
@@ -1309,7 +1318,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         raise ValueError("carved shard streams exist for the fused transport (--transport fused, N > 1)")
     if transport in ("auto", "fused") and world > 1:
         try:
-            prop = FusedPushPropagation(topo, dinv, carve=carve)
+            prop = FusedPushPropagation(topo, dinv, carve=carve, idx16=idx16)
             prop.alloc(4, 1)                                  # peer mappings must be obtainable on this box
         except Exception as e:  # noqa: BLE001
             if transport == "fused":

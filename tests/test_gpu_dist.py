@@ -28,6 +28,8 @@ def worker(rank, world, port, mode, outdir):
         phases, transport = mode.split("/")
         if transport == "fused":
             prop = pd.FusedPushPropagation(topo, dinv)
+        elif transport == "fused16":           # 16-byte index staging with the halo push (not yet run on GPUs)
+            prop = pd.FusedPushPropagation(topo, dinv, idx16=True)
         elif transport == "fusedcarve":        # L2-sized hot column blocks of the shard first (not yet run on GPUs)
             prop = pd.FusedPushPropagation(topo, dinv, carve=dict(block_cols=16384, n_blocks=8, min_piece=8))
         elif transport == "hybrid":            # hub rows summed where their columns live (not yet run on GPUs)
@@ -42,7 +44,7 @@ def worker(rank, world, port, mode, outdir):
         old_of_new = np.argsort(new_of_old)
         mine = old_of_new[lo:hi]
         Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
-        H, Z, S = prop.alloc(F, 3) if transport in ("pipe", "fused", "fusedcarve", "hybrid") else prop.transport.alloc(F, 3)
+        H, Z, S = prop.alloc(F, 3) if transport in ("pipe", "fused", "fused16", "fusedcarve", "hybrid") else prop.transport.alloc(F, 3)
         H.zero_()
         H[: topo.n_local] = torch.from_numpy(Hg[mine]).to(dev)
         out = prop.propagate(H, Z, S, K, alpha).cpu().numpy()
@@ -60,11 +62,11 @@ def worker(rank, world, port, mode, outdir):
 
 
 @pytest.mark.parametrize("mode", ["x/fused", "4/pipe", "1/pipe", "two/push", "one/push", "peer/pull", "peer/p2p", "one/p2p",
-                                  "x/fusedcarve", "64/hybrid", "512/hybrid"])
+                                  "x/fused16", "x/fusedcarve", "64/hybrid", "512/hybrid"])
 def test_partitioned_matches_oracle_on_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if mode.split("/")[1] in ("fusedcarve", "hybrid") and os.environ.get("PPNP_TEST_UNVALIDATED") != "1":
+    if mode.split("/")[1] in ("fused16", "fusedcarve", "hybrid") and os.environ.get("PPNP_TEST_UNVALIDATED") != "1":
         pytest.skip("written after the round's GPU budget was spent; parity-green under gloo only -- set "
                     "PPNP_TEST_UNVALIDATED=1 to run it on GPUs (tools/gpu_calls/r02_first_call.sh does)")
     port = 29700 + len(mode) + (hash(mode) % 40) + (os.getpid() % 50)

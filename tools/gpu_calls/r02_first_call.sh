@@ -21,5 +21,5 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:spmm_stream_kernel --launch-skip 3 --launch-count 1 -o gpurun_out/r02_prof_default -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r02_ncu_default.log 2>&1
 ls -la gpurun_out | tail -8
 # multi-GPU (run with gpurun --gpus 2 / 8): the hybrid exchange and the L2-carved shard streams against the fused default
-#   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus N --steps 3 --warmup 2 [--transport hybrid --hub-degree 64 | --order carve --carve-block-cols 6000000 --carve-blocks 16 --carve-min-piece 16]
+#   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus N --steps 3 --warmup 2 [--dist-idx16 | --transport hybrid --hub-degree 64 | --order carve --carve-block-cols 6000000 --carve-blocks 16 --carve-min-piece 16]
 #   PPNP_TEST_UNVALIDATED=1 timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -q   (2 GPUs)
