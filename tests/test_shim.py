@@ -220,9 +220,17 @@ REFERENCE = "/root/reference"
 def test_sparsegraph_overlay_resolves_like_main_py(monkeypatch):
     """main.py:27-28 imports with [shim, reference] on sys.path: SparseGraph is the GPU-backed subclass,
     ppnp.preprocessing and the data files still come from the reference, and there is no CPU fallback."""
-    for k in [k for k in sys.modules if k == "ppnp" or k.startswith("ppnp.")]:
-        monkeypatch.delitem(sys.modules, k)
+    saved = {k: sys.modules.pop(k) for k in [k for k in sys.modules if k == "ppnp" or k.startswith("ppnp.")]}
     monkeypatch.setattr(sys, "path", [SHIM, REFERENCE] + [p for p in sys.path if p not in (SHIM, REFERENCE)])
+    try:
+        _overlay_checks()
+    finally:                              # leave no overlay modules behind for the tests that follow
+        for k in [k for k in sys.modules if k == "ppnp" or k.startswith("ppnp.") or k == "_ppnp_reference_sparsegraph"]:
+            sys.modules.pop(k, None)
+        sys.modules.update(saved)
+
+
+def _overlay_checks():
     from ppnp.data.sparsegraph import SparseGraph, create_subgraph, largest_connected_components  # noqa: F401
     from ppnp.preprocessing import gen_splits, normalize_attributes  # noqa: F401
     import ppnp.preprocessing as prep
@@ -238,5 +246,3 @@ def test_sparsegraph_overlay_resolves_like_main_py(monkeypatch):
     else:
         g.standardize(select_lcc=True)
         assert g.num_nodes() == 2110 and g.adj_matrix.nnz == 7336
-    for k in [k for k in sys.modules if k == "ppnp" or k.startswith("ppnp.")]:
-        monkeypatch.delitem(sys.modules, k, raising=False)

@@ -58,11 +58,11 @@ def test_oracle_standardize_matches_reference_on_random_graphs():
     import sys
     import warnings
     import scipy.sparse as sp
-    sys.path.insert(0, "/root/reference")
-    try:
-        from ppnp.data.sparsegraph import SparseGraph
-    finally:
-        sys.path.remove("/root/reference")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_reference_sparsegraph_for_tests", "/root/reference/ppnp/data/sparsegraph.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)          # by path: independent of whatever `ppnp` package other tests imported
+    SparseGraph = mod.SparseGraph
     rng = np.random.RandomState(11)
     for trial in range(40):
         n = int(rng.randint(2, 120))
