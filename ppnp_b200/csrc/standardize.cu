@@ -127,31 +127,38 @@ __global__ void hook_kernel(const unsigned long long* __restrict__ ukeys, const 
     }
 }
 
-__global__ void flatten_kernel(int32_t* parent, int32_t* __restrict__ size, int64_t n) {
+// Component of every node = the root of its tree.  The forest is final here (all links were made by
+// hook_kernel, a kernel boundary ago), and this pass only READS it: a walk that shortened paths while
+// another thread stored its root into the same array could overwrite that root with a mere ancestor
+// (round 1's flatten did exactly that and dropped 2 of CiteSeer's 2110 nodes on some runs).  Roots go
+// to a separate array, so the result is a pure function of the forest whatever the interleaving.
+__global__ void flatten_kernel(const int32_t* __restrict__ parent, int32_t* __restrict__ comp,
+                               int32_t* __restrict__ size, int64_t n) {
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t r = find_root(parent, (int32_t)v);
-        parent[v] = r;
-        atomicAdd(size + r, 1);
+        int32_t x = (int32_t)v, p = __ldg(parent + x);
+        while (p != x) { x = p; p = __ldg(parent + x); }
+        comp[v] = x;
+        atomicAdd(size + x, 1);
     }
 }
 
 // (size << 32 | root) over the roots: the largest component, the larger root among equals.
-__global__ void best_component_kernel(const int32_t* __restrict__ parent, const int32_t* __restrict__ size, int64_t n,
+__global__ void best_component_kernel(const int32_t* __restrict__ comp, const int32_t* __restrict__ size, int64_t n,
                                       unsigned long long* __restrict__ best) {
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
-        if (parent[v] == (int32_t)v)
+        if (comp[v] == (int32_t)v)
             atomicMax(best, ((unsigned long long)(unsigned)size[v] << 32) | (unsigned long long)(unsigned)v);
     }
 }
 
 // flag[v] = node is kept; kdeg[v] = its row length if kept.  Entry n of both is 0 (scan totals).
-__global__ void keep_flags_kernel(const int32_t* __restrict__ parent, const unsigned long long* __restrict__ best,
+__global__ void keep_flags_kernel(const int32_t* __restrict__ comp, const unsigned long long* __restrict__ best,
                                   const int64_t* __restrict__ indptr_s, int64_t n, int select_lcc,
                                   int32_t* __restrict__ flag, int64_t* __restrict__ kdeg) {
     const int32_t root = select_lcc ? (int32_t)(*best & 0xffffffffu) : -1;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v <= n; v += (int64_t)gridDim.x * blockDim.x) {
         if (v == n) { flag[n] = 0; kdeg[n] = 0; continue; }
-        const int keep = select_lcc ? (parent[v] == root) : 1;
+        const int keep = select_lcc ? (comp[v] == root) : 1;
         flag[v] = keep;
         kdeg[v] = keep ? (indptr_s[v + 1] - indptr_s[v]) : 0;
     }
@@ -189,7 +196,7 @@ __global__ void write_cols_kernel(const unsigned long long* __restrict__ ukeys, 
 struct Workspace {
     unsigned long long *keys_a, *keys_b;
     int64_t *indptr_s, *kdeg, *kpos, *scalars;   // scalars: [0] number of unique keys, [1] best component (packed)
-    int32_t *parent, *size, *flag, *newid;
+    int32_t *parent, *comp, *size, *flag, *newid;
     void* cub_tmp;
     size_t cub_bytes;
     int64_t total;
@@ -219,6 +226,7 @@ Workspace carve(void* base, int64_t n, int64_t n_keys) {
     w.kpos = reinterpret_cast<int64_t*>(take(8 * (n + 1)));
     w.scalars = reinterpret_cast<int64_t*>(take(16));
     w.parent = reinterpret_cast<int32_t*>(take(4 * n));
+    w.comp = reinterpret_cast<int32_t*>(take(4 * n));
     w.size = reinterpret_cast<int32_t*>(take(4 * n));
     w.flag = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
     w.newid = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
@@ -283,13 +291,13 @@ int ppnp_graph_standardize(const int64_t* indptr, const int32_t* indices, int64_
             hook_kernel<<<grid_for(n_keys), THREADS, 0, stream>>>(ukeys, w.scalars, w.parent, undirected);
             PPNP_CHECK_LAUNCH("hook_kernel");
         }
-        flatten_kernel<<<grid_for(n), THREADS, 0, stream>>>(w.parent, w.size, n);
+        flatten_kernel<<<grid_for(n), THREADS, 0, stream>>>(w.parent, w.comp, w.size, n);
         PPNP_CHECK_LAUNCH("flatten_kernel");
-        best_component_kernel<<<grid_for(n), THREADS, 0, stream>>>(w.parent, w.size, n,
+        best_component_kernel<<<grid_for(n), THREADS, 0, stream>>>(w.comp, w.size, n,
                                                                    reinterpret_cast<unsigned long long*>(w.scalars + 1));
         PPNP_CHECK_LAUNCH("best_component_kernel");
     }
-    keep_flags_kernel<<<grid_for(n + 1), THREADS, 0, stream>>>(w.parent, reinterpret_cast<unsigned long long*>(w.scalars + 1),
+    keep_flags_kernel<<<grid_for(n + 1), THREADS, 0, stream>>>(w.comp, reinterpret_cast<unsigned long long*>(w.scalars + 1),
                                                                w.indptr_s, n, select_lcc, w.flag, w.kdeg);
     PPNP_CHECK_LAUNCH("keep_flags_kernel");
     size_t bytes = w.cub_bytes;

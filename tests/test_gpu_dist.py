@@ -28,11 +28,11 @@ def worker(rank, world, port, mode, outdir):
         phases, transport = mode.split("/")
         if transport == "fused":
             prop = pd.FusedPushPropagation(topo, dinv)
-        elif transport == "fused16":           # 16-byte index staging with the halo push (not yet run on GPUs)
+        elif transport == "fused16":           # 16-byte index staging with the halo push 
             prop = pd.FusedPushPropagation(topo, dinv, idx16=True)
-        elif transport == "fusedcarve":        # L2-sized hot column blocks of the shard first (not yet run on GPUs)
+        elif transport == "fusedcarve":        # L2-sized hot column blocks of the shard first 
             prop = pd.FusedPushPropagation(topo, dinv, carve=dict(block_cols=16384, n_blocks=8, min_piece=8))
-        elif transport == "hybrid":            # hub rows summed where their columns live (not yet run on GPUs)
+        elif transport == "hybrid":            # hub rows summed where their columns live 
             prop = pd.HybridPushPropagation(topo, dinv, hub_degree=int(phases), alpha=alpha)
         elif transport == "pipe":
             prop = pd.PipelinedPushPropagation(topo, dinv, row_groups=int(phases))
@@ -66,9 +66,6 @@ def worker(rank, world, port, mode, outdir):
 def test_partitioned_matches_oracle_on_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    if mode.split("/")[1] in ("fused16", "fusedcarve", "hybrid") and os.environ.get("PPNP_TEST_UNVALIDATED") != "1":
-        pytest.skip("written after the round's GPU budget was spent; parity-green under gloo only -- set "
-                    "PPNP_TEST_UNVALIDATED=1 to run it on GPUs (tools/gpu_calls/r02_first_call.sh does)")
     port = 29700 + len(mode) + (hash(mode) % 40) + (os.getpid() % 50)
     mp.spawn(worker, args=(2, port, mode, str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"ok_{r}") for r in range(2))

@@ -33,7 +33,6 @@ def test_chebyshev_recurrence_reaches_the_reference_matrix_in_numpy():
 
 
 @pytest.mark.gpu
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("mode", ["sym", "rw"])
 def test_ppr_dense_chebyshev_matches_reference_inverse(name, mode):
@@ -53,7 +52,6 @@ def test_ppr_dense_chebyshev_matches_reference_inverse(name, mode):
 
 
 @pytest.mark.gpu
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("K", [1, 2, 3, 6, 7])
 def test_ppr_dense_chebyshev_small_K_matches_numpy_recurrence(K):
     """Odd and even step counts (the result must land in Pi either way), against the recurrence in fp64."""

@@ -10,7 +10,6 @@ from ppnp_b200 import io as pio
 
 
 @pytest.mark.gpu
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("name", ["cora_ml", "citeseer"])
 def test_file_to_normalised_graph_matches_reference_pipeline(tmp_path, name):
     """npz file -> GPU standardise -> GPU calc_A_hat == the reference's main.py:73-75 + helpers.py:58-66."""

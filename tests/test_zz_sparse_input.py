@@ -47,7 +47,6 @@ def test_sparse_input_streams_walk_to_the_dense_products():
 
 
 @pytest.mark.gpu
-@pytest.mark.unvalidated
 @pytest.mark.parametrize("name", ["cora_ml", "citeseer"])
 def test_sparse_first_layer_matches_dense_torch(name):
     z, _ = load_std(name)
@@ -83,7 +82,6 @@ def test_sparse_first_layer_matches_dense_torch(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.unvalidated
 def test_shim_sparse_x_switch_matches_the_dense_encoder(monkeypatch):
     """PPNP_SPARSE_X=1: model.PPNP.forward(X, idx) (model.py:61-63) with the first layer over X's stored
     entries equals the dense encoder in eval mode, and trains (the weight gradient flows) in train mode."""

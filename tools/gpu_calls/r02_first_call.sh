@@ -6,7 +6,7 @@
 #    two-level carves
 # 3. one full ncu capture each of the carved step and its interleaved twin (source view: where the time goes)
 mkdir -p gpurun_out
-PPNP_TEST_UNVALIDATED=1 timeout 300 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/r02_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest.log; tail -4 gpurun_out/r02_pytest.log
+PPNP_TEST_UNVALIDATED=1 timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/r02_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r02_pytest.log; tail -4 gpurun_out/r02_pytest.log
 timeout 200 python bench.py > gpurun_out/r02_bench.log 2>&1; tail -c 1500 gpurun_out/r02_bench.log
 timeout 200 python bench.py --order auto --no-cpu-baseline > gpurun_out/r02_bench_auto.log 2>&1; tail -c 1500 gpurun_out/r02_bench_auto.log
 timeout 120 python tools/bench_standardize.py > gpurun_out/r02_bench_standardize.json 2> gpurun_out/r02_bench_standardize.err; cat gpurun_out/r02_bench_standardize.json
