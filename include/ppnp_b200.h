@@ -166,6 +166,58 @@ int ppnp_appnp_propagate_persistent(const ppnp_plan_t* plan, const float* H, flo
                                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (2b) The same step for the HUB rows of a skewed graph with their accumulators resident in shared
+ *      memory (csrc/appnp_tiled.cu; ppnp_b200/plan.py build_tiled_plan).  No counterpart in the reference
+ *      (north_star subsystem 2: "gathers of Z rows staged through shared memory").
+ *
+ * A CTA owns a group of rows ("slots": a row, or one part of a row too long for one warp) and one slice of
+ * `slice_width` floats of the feature dimension; its warps own disjoint slots and walk their own edge
+ * streams, sorted by (column window, slot, column), in slabs of 32 edges:
+ *   cols[e]        column | PPNP_FLAG on the last edge of a piece (the edges of one slot in one window)
+ *   vals[e]        stored A_hat values (nullable: value-free form)
+ *   slab_meta[2s]  index of the first piece that ends in slab s or later; slab_meta[2s+1] = column window
+ *                  of the slab, numbered from 1 (non-decreasing along a warp's stream; paces the warps of a
+ *                  CTA), bit 30 set when some slot ends twice inside the slab
+ *   piece_slot[p]  CTA-local slot the p-th piece adds to (32 readable spare entries after the last one);
+ *                  padding edges (column 0, no flag) only follow the last piece of a warp
+ *   warp_slab_ptr  [n_ctas * warps_per_cta + 1] slab range of every warp
+ *   cta_slot_ptr   [n_ctas + 1] slot range of every CTA in slot_row
+ *   slot_row[s]    row the slot belongs to; PPNP_FLAG | row for the 2nd.. part of a split row (the parts
+ *                  of a row are consecutive slots of one CTA)
+ *   row_deg[r]     degree (edge count incl. the self loop) of every row, for the epilogue
+ * Rows that own no slot are not written: run the row-major stream over them (ppnp_spmm_step with a plan of
+ * the remaining rows); ppnp_appnp_propagate_tiled does both for K steps.  Results equal ppnp_spmm_step up
+ * to the order of the fp32 additions.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct ppnp_tiled_plan {
+    int64_t n;               /* rows of the matrix                                        */
+    int64_t n_slabs;         /* stream length / 32                                        */
+    int64_t n_pieces;
+    int32_t n_ctas;          /* row groups (grid.x); grid.y = F / slice_width             */
+    int32_t warps_per_cta;   /* 1..16                                                     */
+    int32_t slots_cap;       /* max slots of a CTA (+1 spare)                             */
+    int32_t slack;           /* windows a warp may run ahead of the slowest warp of its CTA */
+    const int32_t* cols;
+    const float* vals;
+    const int32_t* slab_meta;
+    const int32_t* piece_slot;
+    const int32_t* warp_slab_ptr;
+    const int32_t* cta_slot_ptr;
+    const int32_t* slot_row;
+    const float* row_deg;
+} ppnp_tiled_plan_t;
+
+int ppnp_spmm_step_tiled(const ppnp_tiled_plan_t* plan, const float* Zin, const float* T, float* Zout,
+                         int64_t ld, int32_t F, int32_t slice_width, float alpha, int32_t epi,
+                         int32_t use_vals, void* stream);
+/* K steps: hub rows through `hub`, all other rows through the row-major stream `rest` (nullable when
+ * every row is a hub row).  Same arguments and step sequence as ppnp_appnp_propagate. */
+int ppnp_appnp_propagate_tiled(const ppnp_tiled_plan_t* hub, const ppnp_plan_t* rest, const float* H,
+                               float* Z, float* scratch, float* partial, int64_t ld, int32_t F,
+                               int32_t slice_width, int32_t K, float alpha, int32_t mode,
+                               int32_t use_vals, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (3) Exact PPNP.                                      replaces helpers.py:68-71 compute_ppr
  *     Pi = alpha (I - (1-alpha) A_hat)^-1 by power iteration on all n right-hand sides:
  *     Pi_0 = I, Pi_{k+1} = (1-alpha) A_hat Pi_k + alpha I.   A_hat: normalised CSR with fp32

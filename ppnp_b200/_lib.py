@@ -30,6 +30,16 @@ class PlanStruct(C.Structure):
     ]
 
 
+class TiledPlanStruct(C.Structure):
+    """Mirror of ppnp_tiled_plan_t."""
+    _fields_ = [
+        ("n", C.c_int64), ("n_slabs", C.c_int64), ("n_pieces", C.c_int64), ("n_ctas", C.c_int32),
+        ("warps_per_cta", C.c_int32), ("slots_cap", C.c_int32), ("slack", C.c_int32),
+        ("cols", C.c_void_p), ("vals", C.c_void_p), ("slab_meta", C.c_void_p), ("piece_slot", C.c_void_p),
+        ("warp_slab_ptr", C.c_void_p), ("cta_slot_ptr", C.c_void_p), ("slot_row", C.c_void_p), ("row_deg", C.c_void_p),
+    ]
+
+
 _p, _i32, _i64, _f32, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 
 # name -> (restype, argtypes).  Every symbol include/ppnp_b200.h declares is listed here;
@@ -44,6 +54,9 @@ SIGNATURES = {
     "ppnp_spmm_step_push": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _f32, _i32, _i32, _p, _p, _p, _p, _i32, _p]),
     "ppnp_appnp_propagate": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32, _f32, _i32, _i32, _p]),
     "ppnp_appnp_propagate_persistent": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32, _f32, _p]),
+    "ppnp_spmm_step_tiled": (C.c_int, [C.POINTER(TiledPlanStruct), _p, _p, _p, _i64, _i32, _i32, _f32, _i32, _i32, _p]),
+    "ppnp_appnp_propagate_tiled": (C.c_int, [C.POINTER(TiledPlanStruct), C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32,
+                                             _i32, _f32, _i32, _i32, _p]),
     "ppnp_ppr_dense": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),
     "ppnp_ppr_dense_cheb": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),
     "ppnp_gather_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _i32, _p, _i64, _i32, _p]),

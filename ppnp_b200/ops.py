@@ -10,6 +10,7 @@ import torch
 
 from . import _lib
 from .plan import StreamPlan, build_carved_plan, build_stream_plan, degree_order, lane_group_for, lane_transpose
+from .tiled import TiledPlan, build_tiled_plan
 
 MODE = {"sym": _lib.MODE_SYM, "rw": _lib.MODE_RW}
 
@@ -73,12 +74,20 @@ def csr_normalize(indptr, indices, data=None, mode="sym", want_val64=False, want
 class PropagationGraph:
     """Normalised adjacency + edge-stream plan, ready for ``appnp_propagate``."""
 
-    def __init__(self, ahat: NormalizedCSR, chunk_edges=256, order="natural", keep_vals=True, idx16=False, carve=None):
+    def __init__(self, ahat: NormalizedCSR, chunk_edges=256, order="natural", keep_vals=True, idx16=False, carve=None,
+                 tiled=None):
         """order: "natural" | "degree" | a permutation tensor (row-major streams, plan.build_stream_plan) or
         "carve" (hot column blocks first, plan.build_carved_plan; ``carve`` = its keyword arguments).
         idx16: stage the index stream with 16-byte copies from a lane-transposed copy of the stream
-        (feature widths 16 and 64; other widths keep the linear stream)."""
+        (feature widths 16 and 64; other widths keep the linear stream).
+        tiled: keyword arguments of ``tiled.build_tiled_plan`` plus ``slice_width`` (floats of the feature
+        dimension per CTA: 16, 32 or 64): rows of high degree run through the shared-memory-resident kernel
+        (csrc/appnp_tiled.cu), the rest through the row-major stream.  Built per feature width on first use."""
         self.ahat = ahat
+        self.tiled_kw = None if tiled is None else dict(tiled)
+        self._tiled = {}
+        self._keep_vals = bool(keep_vals)
+        self._chunk_edges = int(chunk_edges)
         self.mode = ahat.mode
         vals = ahat.val32 if keep_vals else None
         if isinstance(order, str) and order == "carve":
@@ -110,6 +119,31 @@ class PropagationGraph:
             self._plans16[G] = lane_transpose(self.plan, G)
         return self._plans16[G]
 
+    def tiled_for(self, F):
+        """(TiledPlan, row-major plan of the remaining rows or None, slice width) for feature width F, or None when
+        the graph was not built with ``tiled=`` or F is not a multiple of the slice width."""
+        if self.tiled_kw is None:
+            return None
+        kw = dict(self.tiled_kw)
+        W = int(kw.pop("slice_width", 64))
+        if F % W != 0 or F % 4 != 0:
+            return None
+        if F not in self._tiled:
+            lib = _lib.load()
+            if "n_ctas" not in kw:
+                import ctypes
+                sm = ctypes.c_int32(0)
+                _lib.check(lib.ppnp_device_info(ctypes.byref(sm), None, None, None), "ppnp_device_info")
+                kw["n_ctas"] = max(1, sm.value // (F // W))
+            kw.setdefault("slot_rows", (100 * 1024 - 1024 - 128) // (W * 4) - 1)
+            kw.setdefault("rest_chunk_edges", self._chunk_edges)
+            tp = build_tiled_plan(self.ahat.indptr, self.ahat.indices, self.ahat.val32 if self._keep_vals else None, **kw)
+            rest = tp.rest
+            if rest is not None and self.idx16 and F in (16, 64):
+                rest = lane_transpose(rest, lane_group_for(F))
+            self._tiled[F] = (tp, rest, W)
+        return self._tiled[F]
+
     @classmethod
     def from_adjacency(cls, indptr, indices, data=None, mode="sym", **kw):
         return cls(csr_normalize(indptr, indices, data, mode), **kw)
@@ -123,6 +157,16 @@ class PropagationGraph:
             self._partial[ld] = buf
         return buf
 
+    def rest_partial_buffer(self, rest, ld):
+        if rest is None or rest.n_slots == 0:
+            return None
+        key = ("rest", ld)
+        buf = self._partial.get(key)
+        if buf is None:
+            buf = torch.empty(rest.n_slots * ld, dtype=torch.float32, device=rest.device)
+            self._partial[key] = buf
+        return buf
+
 
 def spmm_step(graph: PropagationGraph, Zin, T, alpha, epi=_lib.EPI_PLAIN, use_vals=True, out=None):
     """One propagation step  out = a * A Zin + b * T  (epilogue ``epi``, include/ppnp_b200.h)."""
@@ -133,6 +177,18 @@ def spmm_step(graph: PropagationGraph, Zin, T, alpha, epi=_lib.EPI_PLAIN, use_va
     n, F = Zin.shape
     if out is None:
         out = torch.empty_like(Zin)
+    tl = graph.tiled_for(F)
+    if tl is not None:
+        tp, rest, W = tl
+        with torch.cuda.device(Zin.device):
+            rc = lib.ppnp_spmm_step_tiled(tp.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), F, F, W, float(alpha), int(epi),
+                                          int(bool(use_vals)), _lib.current_stream())
+            _lib.check(rc, "ppnp_spmm_step_tiled")
+            if rest is not None:
+                rc = lib.ppnp_spmm_step(rest.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), _lib.ptr(graph.rest_partial_buffer(rest, F)),
+                                        F, F, float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
+                _lib.check(rc, "ppnp_spmm_step")
+        return out
     partial = graph.partial_buffer(F)
     with torch.cuda.device(Zin.device):
         rc = lib.ppnp_spmm_step(graph.plan_for(F).struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), _lib.ptr(partial),
@@ -159,6 +215,15 @@ def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False,
         return H.clone()
     Z = out if out is not None else torch.empty_like(H)
     scratch = scratch if scratch is not None else torch.empty_like(H)
+    tl = graph.tiled_for(F)
+    if tl is not None:
+        tp, rest, W = tl
+        with torch.cuda.device(H.device):
+            rc = lib.ppnp_appnp_propagate_tiled(tp.struct(), None if rest is None else rest.struct(), _lib.ptr(H), _lib.ptr(Z),
+                                                _lib.ptr(scratch), _lib.ptr(graph.rest_partial_buffer(rest, F)), F, F, W, int(K),
+                                                float(alpha), MODE[graph.mode], int(bool(use_vals)), _lib.current_stream())
+        _lib.check(rc, "ppnp_appnp_propagate_tiled")
+        return Z
     partial = graph.partial_buffer(F)
     with torch.cuda.device(H.device):
         rc = lib.ppnp_appnp_propagate(graph.plan_for(F).struct(), _lib.ptr(H), _lib.ptr(Z), _lib.ptr(scratch),

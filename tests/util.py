@@ -43,7 +43,7 @@ def epi_coef(epi, alpha, deg):
     raise ValueError(epi)
 
 
-def walk_stream(plan, Zin, T, alpha, epi, use_vals):
+def walk_stream(plan, Zin, T, alpha, epi, use_vals, rows=None):
     """What csrc/appnp_spmm.cu computes from the plan arrays, edge by edge, in numpy fp64.
     Used to test the HOST-side plan logic without a GPU."""
     cols = plan.cols.cpu().numpy()
@@ -93,5 +93,73 @@ def walk_stream(plan, Zin, T, alpha, epi, use_vals):
         a, b = epi_coef(epi, alpha, float(fd[q]))
         out[fr[q]] = a * acc + b * T[fr[q]]
         written[fr[q]] += 1
-    assert (written == 1).all(), "every row must be produced exactly once"
+    if rows is None:
+        assert (written == 1).all(), "every row must be produced exactly once"
+    else:      # a stream over a subset of the rows (plan.build_stream_plan(subset=True))
+        assert (written[rows] == 1).all() and written.sum() == len(rows), "the listed rows exactly once, nothing else"
+    return out
+
+
+def walk_tiled(tp, Zin, T, alpha, epi, use_vals):
+    """What csrc/appnp_tiled.cu computes from a TiledPlan, edge by edge, in numpy fp64 -- and the invariants the
+    kernel relies on (piece counters, windows, no slot ending twice inside a slab, slots owned by one warp).
+    Returns the rows the plan produces (NaN elsewhere)."""
+    cols = tp.cols.cpu().numpy()
+    vals = tp.vals.cpu().numpy() if tp.vals is not None else None
+    meta = tp.slab_meta.cpu().numpy()
+    pslot = tp.piece_slot.cpu().numpy()
+    wptr = tp.warp_slab_ptr.cpu().numpy()
+    cptr = tp.cta_slot_ptr.cpu().numpy()
+    srow = tp.slot_row.cpu().numpy()
+    rdeg = tp.row_deg.cpu().numpy()
+    NW = tp.warps_per_cta
+    F = Zin.shape[1]
+    out = np.full((tp.n, F), np.nan)
+    written = np.zeros(tp.n, dtype=np.int32)
+    for cta in range(tp.n_ctas):
+        ns = int(cptr[cta + 1] - cptr[cta])
+        assert ns + 1 <= tp.slots_cap
+        acc_s = np.zeros((ns + 1, F))
+        owner = np.full(ns + 1, -1)
+        for w in range(NW):
+            s0, s1 = int(wptr[cta * NW + w]), int(wptr[cta * NW + w + 1])
+            if s0 == s1:
+                continue
+            p = int(meta[s0, 0])
+            acc = np.zeros(F)
+            win = 0
+            for s in range(s0, s1):
+                assert int(meta[s, 0]) == p, "slab_meta piece counter out of step"
+                assert (int(meta[s, 1]) & 0x3FFFFFFF) >= win, "windows must not decrease along a warp"
+                win = int(meta[s, 1]) & 0x3FFFFFFF
+                hazard = (int(meta[s, 1]) >> 30) & 1
+                ended = []
+                for e in range(s * 32, s * 32 + 32):
+                    raw = int(cols[e])
+                    acc += (vals[e] if use_vals else 1.0) * Zin[raw & 0x7FFFFFFF]
+                    if raw < 0:
+                        sl = int(pslot[p]); p += 1
+                        assert 0 <= sl <= ns
+                        if sl < ns:
+                            assert owner[sl] in (-1, w), "a slot must belong to one warp"
+                            owner[sl] = w
+                            ended.append(sl)
+                        acc_s[sl] += acc
+                        acc = np.zeros(F)
+                assert hazard == int(len(ended) != len(set(ended))), "slabs in which a slot ends twice must be marked (and only those)"
+        sl = 0
+        while sl < ns:
+            row = int(srow[cptr[cta] + sl])
+            assert row >= 0
+            a = acc_s[sl].copy()
+            t = sl + 1
+            while t < ns and int(srow[cptr[cta] + t]) < 0:
+                assert (int(srow[cptr[cta] + t]) & 0x7FFFFFFF) == row
+                a += acc_s[t]; t += 1
+            ca, cb = epi_coef(epi, alpha, float(rdeg[row]))
+            out[row] = ca * a + cb * T[row]
+            written[row] += 1
+            sl = t
+    hub = tp.hub_rows.cpu().numpy()
+    assert (written[hub] == 1).all() and written.sum() == len(hub), "every hub row exactly once, nothing else"
     return out
