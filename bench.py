@@ -14,6 +14,13 @@ Workloads (BASELINE.json configs):
   rmat100m (N>1 default)  config 5: R-MAT n=100 000 000, ~2 B non-zeros, F=16, rows partitioned
                           over the N GPUs, halo exchange over NCCL each iteration (strong scaling)
   tiny                    a 20 k-node graph for plumbing checks
+  pubmed_exact            config 2: exact PPNP on a PubMed-shape graph (n = 19 717): Pi built on the GPU, then
+                          a step = Pi[idx] @ H forward + its adjoint through the tcgen05 bf16 gather-GEMM
+  pubmed_batch            config 3: batch-main.py's per-batch gather/propagate on the compact top-k Pi, a step
+                          = one sweep over batches of --batch-size random rows
+Every line carries "parity": the results of the timed configuration checked against the CPU oracle after the
+timed region (full-size fp64 C oracle on one GPU; on N GPUs the adjointness identity at full size plus the C
+oracle on a smaller graph through the same partitioned code path).
 --order auto picks the processing order of the edge stream by measurement before the warm-up (degree
 order or an L2-blocked carved order, same results either way; config.order names the one used); the
 default is the measured degree order.
@@ -33,6 +40,8 @@ sys.path.insert(0, ROOT)
 METRIC = "APPNP K=10 propagate edge*feature/s & % HBM roofline at 1/2/4/8 B200 vs CPU ref"
 UNIT = "edge*feature/s"
 ALPHA, KSTEPS = 0.1, 10
+
+PUBMED = {"n": 19717, "nnz_a": 88648, "C": 3, "rows": 940, "k": 128}     # PubMed shape
 
 WORKLOADS = {
     #            n            raw draws      scale  F
@@ -181,40 +190,351 @@ def cpu_torch_sparse_rate(n, F, oip, oidx, oval, k_steps):
 
 def run_reference(args):
     """--impl reference: the CPU implementation of the path on this box's host cores (the oracle
-    port: the reference is pure Python and has no K-step propagation to run)."""
+    port: the reference is pure Python and has no K-step propagation to run).
+    Loads nothing of the product (no CUDA library, no GPU work)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    __import__("__graft_entry__").build()
-    wl = args.workload or "rmat2m"
-    if wl == "rmat100m":
-        wl = "rmat2m"  # host RAM/time: the CPU arm is timed on config 4 (BASELINE.md section 3)
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; this arm uses every host core
+    ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
+    __import__("__graft_entry__").build_oracle()
+    ours_wl = args.workload or ("rmat2m" if args.gpus == 1 else "rmat100m")
+    wl, same = ours_wl, True
+    if ours_wl == "rmat100m":
+        # building the 2 B-edge graph on the host takes longer than the whole bench may run: same recipe and
+        # feature width at 1/6.25 of the nodes (config-5 scale model), said so in the line
+        wl, same = "rmat16m", False
+    if ours_wl in ("pubmed_exact", "pubmed_batch"):
+        return run_reference_pubmed(args, ours_wl, ncpu)
     oracle, n, F, oip, oidx, oval = host_graph(wl)
     cores = oracle.clib().oracle_num_threads()
     k_sample = 2
-    rates = []
-    for _ in range(max(1, args.warmup if args.warmup is not None else 1)):
+    warm = args.warmup if args.warmup is not None else 1
+    for _ in range(max(1, warm)):
         cpu_port_rate(oracle, n, F, oip, oidx, oval, 1, 1)
     steps = args.steps or 3
-    t_total = 0.0
+    rates, t_total = [], 0.0
     for _ in range(steps):
         r, t = cpu_port_rate(oracle, n, F, oip, oidx, oval, k_sample, 1)
         rates.append(r)
         t_total += t
     value = sum(rates) / len(rates)
-    sample = f"{k_sample} of the 20 propagation steps of one pass per bench step ({wl}, nnz(A_hat)={len(oidx)}, F={F})"
+    sample = (f"each bench step = {k_sample} of the 20 propagation steps of one pass on {wl} (nnz(A_hat)={len(oidx)}, F={F}), "
+              f"fp32 OpenMP C port (oracle/ppnp_oracle.c), {cores} threads")
     ts_rate, ts_threads = cpu_torch_sparse_rate(n, F, oip, oidx, oval, 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": args.warmup if args.warmup is not None else 1,
-        "ms_per_step": 1e3 * t_total / steps * (2 * KSTEPS / k_sample), "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl, "n": n, "nnz_a_hat": int(len(oidx)), "F": F, "K": KSTEPS, "alpha": ALPHA,
-                   "pass": "K=10 forward + K=10 backward (extrapolated from the sample)"},
+                   "pass": f"{k_sample} propagation steps per bench step (a sample of the K=10 forward + K=10 backward pass; "
+                           "ms_per_step is the sample's own time, nothing is extrapolated)",
+                   "same_workload": same, "gpu_arm_workload": ours_wl},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "torch_sparse_csr": {"value": ts_rate, "threads": ts_threads, "sample": "1 step"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not same:
+        line["same_workload"] = False
+    print(json.dumps(line))
+
+
+def run_reference_pubmed(args, wl, ncpu):
+    """CPU arm of configs 2/3: the reference's own dense lines (model.py:63 / batch-main.py:140-146) with numpy /
+    torch on the host cores, on the same synthetic PubMed-shape Pi (built by the fp64 oracle)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ppnp_oracle as oracle
+    import torch
+    torch.set_num_threads(ncpu)
+    n, C = PUBMED["n"], PUBMED["C"]
+    rng = np.random.RandomState(0)
+    # a bounded sample: Pi rows for the rows the step touches come from a random dense fp32 matrix of the same
+    # shape (the arithmetic and the bytes are what is timed; the values do not matter for the rate)
+    m = n if wl == "pubmed_exact" else args.batch_size
+    Pi = torch.from_numpy(rng.rand(n, n).astype(np.float32))
+    if wl == "pubmed_batch":
+        Pi[Pi < 1.0 - PUBMED["k"] / n] = 0
+    H = torch.from_numpy(rng.randn(n, C).astype(np.float32))
+    idx = torch.from_numpy(rng.permutation(n)[:m].astype(np.int64))
+    steps = args.steps or 5
+    warm = args.warmup if args.warmup is not None else 1
+
+    def step():
+        if wl == "pubmed_exact":
+            return Pi @ H                       # model.py:65 over all rows, like the GPU arm
+        sub = Pi[idx]
+        sel = (sub > 0).any(dim=0)              # batch-main.py:141
+        return sub[:, sel] @ H[sel]             # batch-main.py:142-146
+    for _ in range(max(1, warm)):
+        step()
+    t = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t) / steps
+    work = m * n * C if wl == "pubmed_exact" else int((Pi[idx] > 0).sum()) * C
+    value = work / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl, "n": n, "C": C, "rows": m, "edge": "one stored entry of the dense Pi rows the step reads"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncpu, "kind": "port",
+                             "sample": "the reference's dense torch lines on the host, random Pi of the same shape"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------- parity / helpers
+def parity_single(ip, idx, H, G, Z, dH, sample_rows=4096):
+    """Full-size check of the timed results against the fp64 C oracle on the host (checker only)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ppnp_oracle as oracle
+    t0 = time.perf_counter()
+    oip, oidx, oval, _ = oracle.c_a_hat(ip.cpu().numpy().astype(np.int64), idx.cpu().numpy(), None, "sym")
+    rows = np.random.RandomState(7).choice(H.shape[0], size=min(sample_rows, H.shape[0]), replace=False)
+    out = {"oracle": "oracle/ppnp_oracle.c (fp64), K=%d alpha=%g, all %d rows" % (KSTEPS, ALPHA, H.shape[0]), "tol": 1e-5}
+    ok = True
+    for name, X, Y in (("fwd", H, Z), ("bwd", G, dH)):
+        ref = oracle.c_appnp_f64(oip, oidx, oval, X.cpu().numpy().astype(np.float64), KSTEPS, ALPHA)
+        got = Y.cpu().numpy().astype(np.float64)
+        rel = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        rel_s = float(np.linalg.norm(got[rows] - ref[rows]) / np.linalg.norm(ref[rows]))
+        mx = float(np.abs(got - ref).max() / np.abs(ref).max())
+        agree = float((got.argmax(1) == ref.argmax(1)).mean())
+        out[name] = {"rel_fro": rel, "rel_fro_%d_sampled_rows" % len(rows): rel_s, "max_abs_over_max": mx, "argmax_agreement": agree}
+        ok = ok and rel < 1e-5 and rel_s < 1e-5
+        del ref, got
+    # adjointness (SURVEY.md 8c KAT-3): <P(H), G> == <H, P(G)>
+    lhs = float((Z.double() * G.double()).sum())
+    rhs = float((H.double() * dH.double()).sum())
+    out["adjointness_rel"] = abs(lhs - rhs) / max(abs(lhs), 1e-30)
+    out["ok"] = bool(ok and out["adjointness_rel"] < 1e-5)
+    out["seconds"] = round(time.perf_counter() - t0, 1)
+    return out
+
+
+def parity_small_partitioned(make_prop, alloc_of, dev, rank, world, F, K, alpha):
+    """The same partitioned code path (same transport, same kernels) on a graph the fp64 C oracle finishes in a
+    second: R-MAT n = 204 800 (tests/test_gpu_dist.py uses the same one), every rank checks its own rows."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ppnp_b200.dist import auto_stripes, build_shard_topology, global_dinv, rmat_shard, stripe_relabel
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ppnp_oracle as oracle       # checker only
+    n, raw, scale = 204_800, 3_000_000, 18
+    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world, batch=1 << 20)
+    dinv = global_dinv(indptr, bounds, rank, world, dev)
+    topo = build_shard_topology(indptr, cols, bounds, rank)
+    pr = make_prop(topo, dinv, None)
+    H, Z, S = alloc_of(pr, 3)
+    new_of_old = stripe_relabel(torch.arange(n), n, world, auto_stripes(n, world)).numpy()
+    mine = np.argsort(new_of_old)[bounds[rank]: bounds[rank + 1]]
+    Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
+    for b in (H, Z, S):
+        b.zero_()
+    H[: topo.n_local] = torch.from_numpy(Hg[mine]).to(dev)
+    out = pr.propagate(H, Z, S, K, alpha).cpu().numpy()
+    ip, idx = oracle.rmat_graph(n, raw, scale, seed=0)
+    oip, oidx, oval, _ = oracle.c_a_hat(ip, idx, None, "sym")
+    ref = oracle.c_appnp_f64(oip, oidx, oval, Hg.astype(np.float64), K, alpha)[mine]
+    err = torch.tensor([float(np.linalg.norm(out - ref) / np.linalg.norm(ref))], device=dev)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    return {"n": n, "F": F, "K": K, "rel_fro_max_over_ranks": float(err), "tol": 1e-5,
+            "oracle": "oracle/ppnp_oracle.c fp64, same recipe as the timed graph"}
+
+
+def sub_bench(argv, gpu_index):
+    """Run this script once more in a fresh process on one GPU and return its JSON line (or the error)."""
+    import subprocess
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID", "MASTER_PORT"):
+        env.pop(k, None)
+    env["MASTER_ADDR"] = "127.0.0.1"
+    env["MASTER_PORT"] = str(29600 + (os.getpid() % 300))
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    env["CUDA_VISIBLE_DEVICES"] = (vis.split(",")[gpu_index] if vis else str(gpu_index))
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=600)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                return {"ms_per_step": d.get("ms_per_step"), "value": d.get("value"), "unit": d.get("unit"),
+                        "workload": d.get("config", {}).get("workload"), "n_gpus": d.get("n_gpus"),
+                        "how": "python bench.py " + " ".join(argv) + " (same box, same run)"}
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
+def _timed_steps(fn, steps, warmup, local):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    clocks = sampler.finish()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return sum(per) / steps, per, clocks
+
+
+def run_pubmed(args, wl, dev, local):
+    """BASELINE.json configs 2 and 3 on one B200: synthetic PubMed-shape graph, Pi built on the
+    GPU (Chebyshev-accelerated multi-RHS iteration), then the timed step:
+      pubmed_exact  logits = Pi @ H over all n rows through the tcgen05 bf16 gather-GEMM (model.py:65), flush-free
+                    because Pi (0.78 GB) is larger than the L2;
+      pubmed_batch  one sweep of 16 batches of --batch-size random rows: support union + propagate on the compact
+                    top-k Pi (batch-main.py:113-117, 140-146)."""
+    import numpy as np
+    import torch
+    import ppnp_b200 as P
+    from ppnp_b200.synth import powerlaw_adjacency
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ppnp_oracle as oracle   # checker only
+    import scipy.sparse as sp
+    n, C = PUBMED["n"], PUBMED["C"]
+    steps = args.steps if args.steps is not None else 20
+    warmup = args.warmup if args.warmup is not None else 3
+    peak, peak_src = measured_peaks()
+    ip, idx = powerlaw_adjacency(n, PUBMED["nnz_a"], seed=0, device=dev)
+    ahat = P.csr_normalize(ip, idx)
+    Kc = P.ppr_cheb_steps_for_tol(ALPHA, 1e-7)
+    torch.cuda.synchronize()
+    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Pi = P.ppr_dense(ahat, ALPHA, K=Kc, method="chebyshev")       # warm-up / result
+    a_.record()
+    Pi = P.ppr_dense(ahat, ALPHA, K=Kc, method="chebyshev")
+    b_.record()
+    torch.cuda.synchronize()
+    build_ms = a_.elapsed_time(b_)
+    build = {"method": "chebyshev", "K": Kc, "ms": build_ms, "algorithmic_bytes": 3 * n * n * 4 * Kc,
+             "frac_of_hbm_peak": 3 * n * n * 4 * Kc / 1e9 / (build_ms * 1e-3) / peak}
+    # oracle: rows of Pi = alpha (I - (1-alpha) A_hat)^-1 (helpers.py:68-71) from the fp64 restatement, KAT-2 of SURVEY 8c
+    # (H = unit vectors reproduces columns of Pi; Pi is symmetric), iterated to round-off
+    adj = sp.csr_matrix((np.ones(int(ip[-1]), np.float32), idx.cpu().numpy(), ip.cpu().numpy()), shape=(n, n))
+    A64 = oracle.calc_A_hat(adj, "sym")
+    probe = np.random.RandomState(5).choice(n, 16, replace=False)
+    E = np.zeros((n, len(probe)))
+    E[probe, np.arange(len(probe))] = 1.0
+    cols_ref = oracle.appnp(A64, E, ALPHA, 400)                 # (1-alpha)^400 ~ 5e-19
+    got = Pi[torch.from_numpy(probe).to(dev)].cpu().numpy().astype(np.float64).T
+    pi_err = float(np.linalg.norm(got - cols_ref) / np.linalg.norm(cols_ref))
+    g = torch.Generator(device=dev).manual_seed(1)
+    H = torch.randn(n, C, device=dev, generator=g)
+    Hh = torch.empty((n, C), dtype=torch.float32, pin_memory=True).copy_(H)
+    Hd = torch.empty_like(H)
+
+    if wl == "pubmed_exact":
+        Pb = P.to_bf16_padded(Pi)
+        step = lambda: P.gather_gemm_bf16(Pb, H, None)
+        ms, per, clocks = _timed_steps(step, steps, warmup, local)
+        out = step()
+        ref_rows = cols_ref.T @ H.cpu().numpy().astype(np.float64)          # oracle logits of the probed rows
+        lg_err = float(np.linalg.norm(out[torch.from_numpy(probe).to(dev)].cpu().numpy() - ref_rows) / np.linalg.norm(ref_rows))
+        out32 = P.gather_gemm(Pi, H, None)
+        lg32 = float(np.linalg.norm(out32[torch.from_numpy(probe).to(dev)].cpu().numpy() - ref_rows) / np.linalg.norm(ref_rows))
+        work = n * n * C
+        algo = n * n * 2 + 2 * n * C * 4
+        outh = torch.empty((n, C), dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            Hd.copy_(Hh, non_blocking=True)
+            outh.copy_(P.gather_gemm_bf16(Pb, Hd, None), non_blocking=True)
+        ms_e2e, _, _ = _timed_steps(e2e_step, max(3, steps // 2), 2, local)
+        launches = 3 * steps      # H pack + tcgen05 gather-GEMM + slice reduction per apply
+        cpu = None
+        if not args.no_cpu_baseline:
+            Pi_h = Pi.cpu().numpy()
+            H_h = H.cpu().numpy()
+            m = 4096
+            t0 = time.perf_counter()
+            for _ in range(3):
+                Pi_h[:m] @ H_h
+            dt = (time.perf_counter() - t0) / 3
+            cpu = {"value": m * n * C / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"model.py:65 with numpy fp32 on the host: the first {m} rows of the same Pi @ H"}
+        extra = {"pi_build": build, "fp32_path_rel_err_vs_oracle_rows": lg32}
+        for N in (16, 64):
+            HN = torch.randn(n, N, device=dev, generator=g)
+            t, _, _ = _timed_steps(lambda: P.gather_gemm_bf16(Pb, HN, None), 10, 2, local)
+            extra[f"apply_N{N}_ms"] = t
+            extra[f"apply_N{N}_frac_of_hbm_peak"] = n * n * 2 / 1e9 / (t * 1e-3) / peak
+        parity = {"pi_rows_vs_oracle_rel_fro": pi_err, "logits_bf16_vs_oracle_rel_fro": lg_err, "tol_pi": 1e-5, "tol_bf16": 1e-2,
+                  "oracle": "oracle/ppnp_oracle.py fp64 (helpers.py:58-71 restated; 16 probed rows)",
+                  "ok": bool(pi_err < 1e-5 and lg_err < 1e-2 and lg32 < 1e-5)}
+        config = {"workload": wl, "n": n, "nnz_a": int(ip[-1]), "C": C, "rows": n, "alpha": ALPHA,
+                  "edge": "one stored entry of the dense Pi", "pass": "logits = Pi @ H, bf16 operands, fp32 accumulate in TMEM",
+                  "l2": "Pi (0.78 GB bf16) larger than L2"}
+        kernel, dtype = "gather_gemm_tc_kernel", "bf16"
+        h2d, d2h = n * C * 4, n * C * 4
+    else:
+        k, B, nb = PUBMED["k"], args.batch_size, 16
+        P.topk_sparsify_(Pi, k)
+        spp = P.dense_to_sparse_ppr(Pi)
+        batches = [torch.randperm(n, device=dev, generator=g)[:B].sort().values for _ in range(nb)]
+
+        def step():
+            for ib in batches:
+                sel = P.batch_support(spp, ib)
+                P.batch_propagate(spp, ib, sel, H[sel])
+        ms, per, clocks = _timed_steps(step, steps, warmup, local)
+        kept = sum(int((spp.indptr[ib + 1] - spp.indptr[ib]).sum()) for ib in batches)
+        work = kept * C
+        algo = kept * 8 + sum(int(P.batch_support(spp, ib).sum()) for ib in batches) * C * 4 + nb * B * C * 4
+        # parity: the literal batch lines (batch-main.py:140-146) in the oracle on the host, first batch
+        ib = batches[0]
+        sel = P.batch_support(spp, ib)
+        ours = P.batch_propagate(spp, ib, sel, H[sel]).cpu().numpy()
+        lit = oracle.batch_step(Pi.cpu().numpy(), ib.cpu().numpy(), H.cpu().numpy())
+        lit_logits = lit[0] if isinstance(lit, tuple) else lit
+        b_err = float(np.linalg.norm(ours - lit_logits) / np.linalg.norm(lit_logits))
+        outh = torch.empty((B, C), dtype=torch.float32, pin_memory=True)
+
+        def e2e_step():
+            Hd.copy_(Hh, non_blocking=True)
+            for ib_ in batches:
+                s_ = P.batch_support(spp, ib_)
+                outh.copy_(P.batch_propagate(spp, ib_, s_, Hd[s_]), non_blocking=True)
+        ms_e2e, _, _ = _timed_steps(e2e_step, max(3, steps // 2), 2, local)
+        launches = 3 * nb * steps
+        cpu = None
+        if not args.no_cpu_baseline:
+            Pi_h, H_h = Pi.cpu(), H.cpu()
+            t0 = time.perf_counter()
+            for ib_ in batches[:4]:
+                sub = Pi_h[ib_.cpu()]
+                s_ = (sub > 0).any(dim=0)
+                sub[:, s_] @ H_h[s_]
+            dt = (time.perf_counter() - t0) / 4 * nb
+            cpu = {"value": work / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": "batch-main.py:140-146 with torch on the host, 4 of the 16 batches"}
+        extra = {"pi_build": build, "kept_entries": int(spp.indices.numel()), "batches_per_s": nb / (ms * 1e-3)}
+        parity = {"pi_rows_vs_oracle_rel_fro": pi_err, "batch_logits_vs_oracle_rel_fro": b_err, "tol": 1e-5,
+                  "oracle": "oracle/ppnp_oracle.py batch_step (batch-main.py:140-146 restated)", "ok": bool(pi_err < 1e-5 and b_err < 1e-5)}
+        config = {"workload": wl, "n": n, "nnz_a": int(ip[-1]), "C": C, "k": k, "batch_size": B, "batches_per_step": nb,
+                  "edge": "one kept entry of the top-k Pi rows of a batch", "pass": "support union + compact gather/propagate per batch",
+                  "l2": "latency-bound: working set fits the L2"}
+        kernel, dtype = "batch_propagate_kernel", "f32"
+        h2d, d2h = n * C * 4, nb * B * C * 4
+    achieved = algo / (ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": work / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": config,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": kernel, "algorithmic_bytes_per_step": algo},
+            "cpu_baseline": cpu,
+            "e2e": {"value": work / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks, "ms_per_step_minmax": [min(per), max(per)], "parity": parity, "extra": extra}
     print(json.dumps(line))
 
 
@@ -231,6 +551,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     wl = args.workload or ("rmat2m" if world == 1 else "rmat100m")
+    if wl in ("pubmed_exact", "pubmed_batch"):
+        if world != 1:
+            raise SystemExit("the PubMed-shape workloads run on one GPU (replicas only: independent batches / row blocks)")
+        __import__("__graft_entry__").build()
+        return run_pubmed(args, wl, dev, local)
     # config 5 family: always through the partitioned code path, also at N=1, so that T_1 and T_P of the
     # scaling study come from the same code
     partitioned = world > 1 or wl in ("rmat100m", "rmat16m")
@@ -257,7 +582,9 @@ def run_ours(args):
                                        phases=args.phases, transport=args.transport, stripes=args.stripes,
                                        row_groups=args.row_groups, hub_degree=args.hub_degree, idx16=args.dist_idx16,
                                        carve=({"block_cols": args.carve_block_cols, "n_blocks": args.carve_blocks,
-                                               "min_piece": args.carve_min_piece} if args.order == "carve" else None))
+                                               "min_piece": args.carve_min_piece} if args.order == "carve" else None),
+                                       check_small=(None if args.no_parity else
+                                                    (lambda mk, al: parity_small_partitioned(mk, al, dev, rank, world, F, KSTEPS, ALPHA))))
         if rank == 0:
             sampler_clocks = result.pop("clocks")
             nnz = result.pop("nnz")
@@ -276,11 +603,25 @@ def run_ours(args):
                              "unit": "GB/s", "frac": bytes_pass / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None,
                              "peak_source": peak_src + f" x {world} GPUs", "kernel": "spmm_stream_kernel"},
                 "e2e": result.pop("e2e"), "gpu_launches": result.pop("gpu_launches"), "clocks": sampler_clocks,
-                "extra": dict(result, n1_same_workload=n1_reference(wl)),
+                "parity": result.pop("parity"),
+                "extra": dict(result, n1_committed_round1=n1_reference(wl)),
             }
-            print(json.dumps(line))
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0:
+            if world > 1 and not args.no_extras:
+                # T_1 of the SAME workload through the same code path, measured now on this rank's GPU (the other
+                # ranks have left): the parallel efficiency below uses nothing but numbers of this run
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                t1 = sub_bench(["--gpus", "1", "--workload", wl, "--steps", "2", "--warmup", "1", "--no-cpu-baseline",
+                                "--no-extras", "--no-parity"], local)
+                line["extra"]["t1_live"] = t1
+                if t1.get("ms_per_step"):
+                    line["extra"]["efficiency"] = {"value": t1["ms_per_step"] / (world * ms), "formula": "T_1 / (N * T_N), strong scaling, "
+                                                   "T_1 measured in this run on one GPU of this box (extra.t1_live)"}
+            print(json.dumps(line))
         return
 
     # ---------------------------------------------------------------- single GPU: config 4
@@ -330,7 +671,12 @@ def run_ours(args):
         del best
         torch.cuda.empty_cache()
     else:
-        graph = P.PropagationGraph(ahat, chunk_edges=args.chunk_edges, order=args.order, idx16=args.idx16, carve=carve)
+        tiled = None
+        if args.tiled:
+            tiled = {"slice_width": args.tiled_slice, "slack": args.tiled_slack, "fine_cols": args.tiled_fine_cols,
+                     "rest": "rows" if args.rows_below else "stream"}
+        graph = P.PropagationGraph(ahat, chunk_edges=args.chunk_edges, order=args.order, idx16=args.idx16, carve=carve, tiled=tiled,
+                                   rows_below=(args.rows_below or None) if not args.tiled else None)
     nnz = ahat.nnz
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
@@ -427,6 +773,27 @@ def run_ours(args):
     ms_e2e = e0.elapsed_time(e1) / e2e_steps
     assert torch.equal(Zh, Z.cpu()) and torch.equal(dHh, dH.cpu())      # the results did reach the host
 
+    # ---- parity of exactly what was timed: Z = P(H) and dH = P(G) of the last pass against the fp64 C oracle
+    # (oracle/ppnp_oracle.c: calc_A_hat restated from helpers.py:58-63 + the K-step recurrence), every row
+    parity = None
+    if not args.no_parity:
+        parity = parity_single(ip, idx, H, G, Z, dH)
+
+    if graph.rows_part is not None:
+        launches_per_pass = 2 * KSTEPS * ((0 if graph.plan is None else (2 if graph.plan.n_fix > 0 else 1)) + 1)
+    tl = graph.tiled_for(F)
+    if tl is not None:
+        launches_per_pass = 2 * KSTEPS * (1 + (0 if tl[1] is None else (2 if tl[1].n_fix > 0 else 1)) + (0 if tl[3] is None else 1))
+
+    extra = {}
+    if wl == "rmat2m" and not args.no_extras:
+        # T_1 of the multi-GPU workload (config 5) through the partitioned code path, measured in this run on this
+        # box: the denominator of the parallel efficiency of the N > 1 lines
+        del Hh, Gh, Zh, dHh, Hd, Gd
+        torch.cuda.empty_cache()
+        extra["rmat100m_n1"] = sub_bench(["--gpus", "1", "--workload", "rmat100m", "--steps", "2", "--warmup", "1",
+                                          "--no-cpu-baseline", "--no-extras", "--no-parity"], local)
+
     # ---- CPU baseline beside it (rank 0, bounded sample)
     cpu = None
     if not args.no_cpu_baseline:
@@ -452,7 +819,8 @@ def run_ours(args):
                    "pass": "K=10 forward + K=10 backward = 20 fused SpMM+teleport launches",
                    "form": "stored values" if args.use_vals else "value-free Y-space (stored values in step 1)",
                    "order": args.order, "chunk_edges": args.chunk_edges, "l2": "inputs larger than L2 (3 x 512 MB)",
-                   "idx16": bool(args.idx16), "carve": graph.plan.carve,
+                   "idx16": bool(args.idx16), "carve": None if graph.plan is None else graph.plan.carve,
+                   "rows_below": args.rows_below or None,
                    "order_candidates_ms_per_launch": order_tried,
                    "graph_build_s": round(t_build, 2)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -465,7 +833,12 @@ def run_ours(args):
         "gpu_launches": launches_per_pass * steps,
         "clocks": clocks,
         "ms_per_step_minmax": [min(per), max(per)],
+        "parity": parity,
+        "extra": extra,
     }
+    if tl is not None:
+        line["config"]["tiled"] = dict(tl[0].stats, slice_width=tl[2])
+        line["roofline"]["kernel"] = "spmm_tiled_kernel + spmm_stream_kernel"
     print(json.dumps(line))
 
 
@@ -475,7 +848,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["pubmed_exact", "pubmed_batch"])
     ap.add_argument("--order", default="degree", choices=["auto", "natural", "degree", "carve"],
                     help="processing order of the edge stream; auto times degree order and two L2-blocked carves and keeps the fastest")
     ap.add_argument("--idx16", dest="idx16", action="store_true", default=True,
@@ -490,6 +863,17 @@ def main():
     ap.add_argument("--chunk-edges", type=int, default=256)
     ap.add_argument("--use-vals", action="store_true", help="stored-value form in every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed results")
+    ap.add_argument("--no-extras", action="store_true", help="skip the companion measurements (T_1 of config 5 in the N=1 run, live T_1 in the N>1 runs)")
+    ap.add_argument("--tiled", dest="tiled", action="store_true", default=False,
+                    help="hub rows through the shared-memory-resident kernel (csrc/appnp_tiled.cu)")
+    ap.add_argument("--no-tiled", dest="tiled", action="store_false")
+    ap.add_argument("--rows-below", type=int, default=0,
+                    help="rows with fewer stored entries go through the one-lane-group-per-row kernel (csrc/appnp_rows.cu); 0 = off")
+    ap.add_argument("--tiled-slice", type=int, default=64, choices=[16, 32, 64], help="--tiled: floats of the feature dimension per CTA")
+    ap.add_argument("--tiled-slack", type=int, default=1)
+    ap.add_argument("--tiled-fine-cols", type=int, default=256)
+    ap.add_argument("--batch-size", type=int, default=128, help="pubmed_batch: rows per batch (batch-main.py:52 default)")
     ap.add_argument("--phases", default="one", choices=["peer", "two", "one"], help="multi-GPU: how a step is split")
     ap.add_argument("--row-groups", type=int, default=4, help="multi-GPU: kernels per step of the pipelined push")
     ap.add_argument("--stripes", type=int, default=0, help="multi-GPU: block-cyclic stripes per rank (0 = auto, ~4096-id stripes; 1 = plain contiguous blocks)")

@@ -185,8 +185,8 @@ int ppnp_appnp_propagate_persistent(const ppnp_plan_t* plan, const float* H, flo
  *   slot_row[s]    row the slot belongs to; PPNP_FLAG | row for the 2nd.. part of a split row (the parts
  *                  of a row are consecutive slots of one CTA)
  *   row_deg[r]     degree (edge count incl. the self loop) of every row, for the epilogue
- * Rows that own no slot are not written: run the row-major stream over them (ppnp_spmm_step with a plan of
- * the remaining rows); ppnp_appnp_propagate_tiled does both for K steps.  Results equal ppnp_spmm_step up
+ * Rows that own no slot are not written: run one of the other kernels over them (ppnp_spmm_step with a plan of
+ * the remaining rows, or ppnp_spmm_step_rows); ppnp_appnp_propagate_parts does that for K steps.  Results equal ppnp_spmm_step up
  * to the order of the fp32 additions.
  * ---------------------------------------------------------------------------------------- */
 typedef struct ppnp_tiled_plan {
@@ -210,12 +210,36 @@ typedef struct ppnp_tiled_plan {
 int ppnp_spmm_step_tiled(const ppnp_tiled_plan_t* plan, const float* Zin, const float* T, float* Zout,
                          int64_t ld, int32_t F, int32_t slice_width, float alpha, int32_t epi,
                          int32_t use_vals, void* stream);
-/* K steps: hub rows through `hub`, all other rows through the row-major stream `rest` (nullable when
- * every row is a hub row).  Same arguments and step sequence as ppnp_appnp_propagate. */
-int ppnp_appnp_propagate_tiled(const ppnp_tiled_plan_t* hub, const ppnp_plan_t* rest, const float* H,
-                               float* Z, float* scratch, float* partial, int64_t ld, int32_t F,
-                               int32_t slice_width, int32_t K, float alpha, int32_t mode,
-                               int32_t use_vals, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * (2c) The same step for rows of LOW degree, one lane group per row, straight off the normalised CSR
+ *      (csrc/appnp_rows.cu): no edge stream, no flags, no partial sums.  rows[0 .. n_rows) lists the rows to
+ *      produce (any subset of [0, n), best in descending degree); indptr / indices / vals are the CSR of
+ *      A_hat (vals nullable: value-free form, the degree of a row is its number of stored entries).  The
+ *      push arguments are those of ppnp_spmm_step_push (all NULL / 0: no halo push).
+ * ---------------------------------------------------------------------------------------- */
+int ppnp_spmm_step_rows(const int32_t* indptr, const int32_t* indices, const float* vals,
+                        const int32_t* rows, int64_t n_rows, int64_t n, const float* Zin, const float* T,
+                        float* Zout, int64_t ld, int32_t F, float alpha, int32_t epi, int32_t use_vals,
+                        const int32_t* push_ptr, const int32_t* push_code, const int32_t* push_first,
+                        const void* const* peer_bases_host, int32_t n_peers, void* stream);
+
+typedef struct ppnp_rows_plan {
+    int64_t n;               /* rows of the matrix                 */
+    int64_t n_rows;          /* rows this part produces            */
+    const int32_t* indptr;   /* [n + 1] CSR of A_hat               */
+    const int32_t* indices;
+    const float* vals;       /* nullable                           */
+    const int32_t* rows;     /* [n_rows]                           */
+} ppnp_rows_plan_t;
+
+/* K steps from Z_0 = H with the rows of the matrix split over up to three kernels by degree: `tiled` (hub
+ * rows, shared-memory accumulators), `stream_plan` (row-major edge stream) and `rows` (one lane group per
+ * row); each part is nullable, together they must produce every row exactly once.  Same step sequence,
+ * epilogues and arguments as ppnp_appnp_propagate (partial: the stream part's partial-sum buffer). */
+int ppnp_appnp_propagate_parts(const ppnp_tiled_plan_t* tiled, const ppnp_plan_t* stream_plan,
+                               const ppnp_rows_plan_t* rows, const float* H, float* Z, float* scratch,
+                               float* partial, int64_t ld, int32_t F, int32_t slice_width, int32_t K,
+                               float alpha, int32_t mode, int32_t use_vals, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (3) Exact PPNP.                                      replaces helpers.py:68-71 compute_ppr

@@ -40,6 +40,12 @@ class TiledPlanStruct(C.Structure):
     ]
 
 
+class RowsPlanStruct(C.Structure):
+    """Mirror of ppnp_rows_plan_t."""
+    _fields_ = [("n", C.c_int64), ("n_rows", C.c_int64), ("indptr", C.c_void_p), ("indices", C.c_void_p),
+                ("vals", C.c_void_p), ("rows", C.c_void_p)]
+
+
 _p, _i32, _i64, _f32, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64
 
 # name -> (restype, argtypes).  Every symbol include/ppnp_b200.h declares is listed here;
@@ -55,8 +61,9 @@ SIGNATURES = {
     "ppnp_appnp_propagate": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32, _f32, _i32, _i32, _p]),
     "ppnp_appnp_propagate_persistent": (C.c_int, [C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32, _f32, _p]),
     "ppnp_spmm_step_tiled": (C.c_int, [C.POINTER(TiledPlanStruct), _p, _p, _p, _i64, _i32, _i32, _f32, _i32, _i32, _p]),
-    "ppnp_appnp_propagate_tiled": (C.c_int, [C.POINTER(TiledPlanStruct), C.POINTER(PlanStruct), _p, _p, _p, _p, _i64, _i32, _i32,
-                                             _i32, _f32, _i32, _i32, _p]),
+    "ppnp_spmm_step_rows": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _f32, _i32, _i32, _p, _p, _p, _p, _i32, _p]),
+    "ppnp_appnp_propagate_parts": (C.c_int, [C.POINTER(TiledPlanStruct), C.POINTER(PlanStruct), C.POINTER(RowsPlanStruct), _p, _p, _p, _p,
+                                             _i64, _i32, _i32, _i32, _f32, _i32, _i32, _p]),
     "ppnp_ppr_dense": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),
     "ppnp_ppr_dense_cheb": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),
     "ppnp_gather_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _i32, _p, _i64, _i32, _p]),

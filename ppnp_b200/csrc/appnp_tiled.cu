@@ -307,32 +307,4 @@ int ppnp_spmm_step_tiled(const ppnp_tiled_plan_t* plan, const float* Zin, const 
 #undef PPNP_TGO
 }
 
-int ppnp_appnp_propagate_tiled(const ppnp_tiled_plan_t* hub, const ppnp_plan_t* rest, const float* H, float* Z, float* scratch,
-                               float* partial, int64_t ld, int32_t F, int32_t slice_width, int32_t K, float alpha, int32_t mode,
-                               int32_t use_vals, void* stream) {
-    using namespace ppnp;
-    PPNP_REQUIRE(H && Z && scratch && H != Z && H != scratch && Z != scratch, "H, Z, scratch must be distinct buffers");
-    PPNP_REQUIRE(K >= 1, "K >= 1");
-    PPNP_REQUIRE(mode == PPNP_MODE_SYM || mode == PPNP_MODE_RW, "bad mode");
-    const float* src = H;
-    for (int k = 1; k <= K; ++k) {
-        float* dst = ((K - k) % 2 == 0) ? Z : scratch;
-        int epi, vals;
-        if (use_vals) { epi = PPNP_EPI_PLAIN; vals = 1; }
-        else if (mode == PPNP_MODE_RW) { epi = PPNP_EPI_RW; vals = 0; }
-        else if (K == 1) { epi = PPNP_EPI_PLAIN; vals = 1; }
-        else if (k == 1) { epi = PPNP_EPI_Z2Y; vals = 1; }
-        else if (k == K) { epi = PPNP_EPI_Y2Z; vals = 0; }
-        else { epi = PPNP_EPI_Y; vals = 0; }
-        int rc = ppnp_spmm_step_tiled(hub, src, H, dst, ld, F, slice_width, alpha, epi, vals, stream);
-        if (rc) return rc;
-        if (rest != nullptr) {
-            rc = ppnp_spmm_step(rest, src, H, dst, partial, ld, F, alpha, epi, vals, stream);
-            if (rc) return rc;
-        }
-        src = dst;
-    }
-    return PPNP_OK;
-}
-
 }  // extern "C"

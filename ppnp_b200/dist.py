@@ -43,13 +43,13 @@ _FLAGS = {}
 def rank_barrier(handle, device, group=None):
     """Stream-ordered barrier across the ranks between two propagation steps: everything enqueued on
     the current stream before it (kernels that stored into peers' memory included) has completed on
-    EVERY rank before anything enqueued after it starts.  Default: a 4-byte NCCL all-reduce (measured
-    correct for the in-kernel peer stores); PPNP_DIST_BARRIER=symm uses the symmetric-memory signal
-    barrier instead (faster, but it let a rank run ahead in the fused-push tests on 2 GPUs)."""
+    EVERY rank before anything enqueued after it starts: a 4-byte NCCL all-reduce (measured correct for
+    the in-kernel peer stores).  The symmetric-memory signal barrier was faster but let a rank run ahead in
+    the fused-push tests on 2 GPUs; it is not selectable any more (PPNP_DIST_BARRIER=symm raises)."""
     import os
-    if os.environ.get("PPNP_DIST_BARRIER", "nccl") == "symm" and handle is not None:
-        handle.barrier()
-        return
+    if os.environ.get("PPNP_DIST_BARRIER", "nccl") != "nccl":
+        raise RuntimeError("PPNP_DIST_BARRIER: only the NCCL barrier is supported (the symmetric-memory signal barrier "
+                           "let ranks run ahead of in-kernel peer stores and was removed)")
     key = (device, id(group))
     flag = _FLAGS.get(key)
     if flag is None:
@@ -876,6 +876,11 @@ class FusedPushPropagation:
         t = self.topo
         multi = t.world > 1
         if multi:
+            if K == 1:
+                # the only step of a K = 1 call reads the halo of its INPUT; with K >= 2 the last step reads the
+                # halo of the previous iterate, so a peer that has already started its next call (and pushes that
+                # call's input) cannot overwrite rows this rank still gathers.  For K = 1 order the calls explicitly.
+                self._barrier(H_ext)
             self._push_input(H_ext)
         src = H_ext
         for k in range(1, K + 1):
@@ -1303,7 +1308,7 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
 
 
 def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4,
-                      carve=None, hub_degree=64, idx16=False):
+                      carve=None, hub_degree=64, idx16=False, check_small=None):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
@@ -1316,28 +1321,35 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     del cols
     if carve and not (transport in ("auto", "fused") and world > 1):
         raise ValueError("carved shard streams exist for the fused transport (--transport fused, N > 1)")
-    if transport in ("auto", "fused") and world > 1:
-        try:
-            prop = FusedPushPropagation(topo, dinv, carve=carve, idx16=idx16)
-            prop.alloc(4, 1)                                  # peer mappings must be obtainable on this box
-        except Exception as e:  # noqa: BLE001
-            if transport == "fused":
-                raise
-            import warnings
-            warnings.warn(f"peer-memory transport unavailable ({type(e).__name__}: {e}); falling back to NCCL point-to-point")
-            prop = PartitionedPropagation(topo, dinv, phases="one", transport="p2p")
-    elif transport == "hybrid" and world > 1:
-        prop = HybridPushPropagation(topo, dinv, hub_degree=hub_degree, alpha=alpha)
-    elif transport == "pipe" and world > 1:
-        prop = PipelinedPushPropagation(topo, dinv, row_groups=row_groups)
-    else:
-        prop = PartitionedPropagation(topo, dinv, phases=phases, transport=("p2p" if transport in ("pipe", "fused", "hybrid") else transport))
+
+    def make_prop(topo_, dinv_, carve_):
+        if transport in ("auto", "fused") and world > 1:
+            try:
+                pr = FusedPushPropagation(topo_, dinv_, carve=carve_, idx16=idx16)
+                pr.alloc(4, 1)                                  # peer mappings must be obtainable on this box
+                return pr
+            except Exception as e:  # noqa: BLE001
+                if transport == "fused":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory transport unavailable ({type(e).__name__}: {e}); falling back to NCCL point-to-point")
+                return PartitionedPropagation(topo_, dinv_, phases="one", transport="p2p")
+        if transport == "hybrid" and world > 1:
+            return HybridPushPropagation(topo_, dinv_, hub_degree=hub_degree, alpha=alpha)
+        if transport == "pipe" and world > 1:
+            return PipelinedPushPropagation(topo_, dinv_, row_groups=row_groups)
+        return PartitionedPropagation(topo_, dinv_, phases=phases, transport=("p2p" if transport in ("pipe", "fused", "hybrid") else transport))
+
+    def alloc_of(pr, count):
+        return pr.alloc(F, count) if isinstance(pr, _PUSH_CLASSES) else pr.transport.alloc(F, count)
+
+    prop = make_prop(topo, dinv, carve)
     del dinv
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
-    H, G, Z, S = (prop.alloc(F, 4) if isinstance(prop, _PUSH_CLASSES) else prop.transport.alloc(F, 4))
+    H, G, Z, S, Z2 = alloc_of(prop, 5)
     g = torch.Generator(device=dev).manual_seed(1 + rank)
-    for b in (H, G, Z, S):
+    for b in (H, G, Z, S, Z2):
         b.zero_()
     H[: topo.n_local].normal_(generator=g)
     G[: topo.n_local].normal_(generator=g)
@@ -1364,26 +1376,77 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 
-    # e2e: host shards in, host results out
-    Hh = torch.empty((topo.n_local, F), dtype=torch.float32, pin_memory=True).copy_(H[: topo.n_local])
-    Zh = torch.empty((topo.n_local, F), dtype=torch.float32, pin_memory=True)
+    # ---- parity at full size: adjointness <P(H), G> == <H, P(G)> over all ranks (A_hat is symmetric; a halo row that
+    # failed to arrive, a wrong push list or a wrong degree breaks it), fp64 dot products, all-reduced
+    nl = topo.n_local
+    zf = prop.propagate(H, Z, S, K, alpha)
+    lhs = (zf.double() * G[:nl].double()).sum()
+    zb = prop.propagate(G, Z2, S, K, alpha)
+    rhs = (H[:nl].double() * zb.double()).sum()
+    dots = torch.stack([lhs, rhs])
+    dist.all_reduce(dots)
+    adj_rel = float((dots[0] - dots[1]).abs() / dots[0].abs().clamp_min(1e-30))
+
+    # ---- e2e: host shards in, host results out; copy-in, compute and copy-out on three streams like the one-GPU arm
+    # (the next input rides under the running propagation, the previous result leaves under the next one)
+    Hh = torch.empty((nl, F), dtype=torch.float32, pin_memory=True).copy_(H[:nl])
+    Gh = torch.empty((nl, F), dtype=torch.float32, pin_memory=True).copy_(G[:nl])
+    Zh = torch.empty((nl, F), dtype=torch.float32, pin_memory=True)
+    dHh = torch.empty((nl, F), dtype=torch.float32, pin_memory=True)
+    s_in, s_out, cur = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
+    last = {"fwd": None, "bwd": None, "z": None, "dh": None}
 
     def one_pass_e2e():
-        for _ in range(2):
-            H[: topo.n_local].copy_(Hh, non_blocking=True)
-            prop.propagate(H, Z, S, K, alpha)
-            Zh.copy_(Z[: topo.n_local], non_blocking=True)
+        with torch.cuda.stream(s_in):
+            if last["fwd"] is not None:
+                s_in.wait_event(last["fwd"])              # H is free once the previous forward has finished with it
+            H[:nl].copy_(Hh, non_blocking=True)
+            eH = torch.cuda.Event(); eH.record(s_in)
+            if last["bwd"] is not None:
+                s_in.wait_event(last["bwd"])
+            G[:nl].copy_(Gh, non_blocking=True)
+            eG = torch.cuda.Event(); eG.record(s_in)
+        cur.wait_event(eH)
+        if last["z"] is not None:
+            cur.wait_event(last["z"])                     # Z is free once its previous read-back has finished
+        prop.propagate(H, Z, S, K, alpha)
+        f = torch.cuda.Event(); f.record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(f)
+            Zh.copy_(Z[:nl], non_blocking=True)
+            zo = torch.cuda.Event(); zo.record(s_out)
+        cur.wait_event(eG)
+        if last["dh"] is not None:
+            cur.wait_event(last["dh"])
+        prop.propagate(G, Z2, S, K, alpha)
+        b = torch.cuda.Event(); b.record(cur)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(b)
+            dHh.copy_(Z2[:nl], non_blocking=True)
+            do = torch.cuda.Event(); do.record(s_out)
+        last.update(fwd=f, bwd=b, z=zo, dh=do)
+
+    def drain():
+        cur.wait_stream(s_in)
+        cur.wait_stream(s_out)
 
     one_pass_e2e()
+    drain()
     torch.cuda.synchronize()
     dist.barrier()
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    e2e_steps = 3
     e0.record()
-    for _ in range(2):
+    for _ in range(e2e_steps):
         one_pass_e2e()
+    drain()
     e1.record()
     torch.cuda.synchronize()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1) / 2], device=dev)
+    ms_e2e = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device=dev)
     dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    e2e_ok = bool(torch.equal(Zh, Z[:nl].cpu()) and torch.equal(dHh, Z2[:nl].cpu()))
+    del Hh, Gh, Zh, dHh
 
     # diagnostics: the transfers alone and the compute alone (not part of the headline number)
     def timed(fn, reps=4):
@@ -1440,7 +1503,12 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     if isinstance(prop, _PUSH_CLASSES):
         launches += (world - 1) * getattr(prop, "G", 0)
     work = 2 * K * nnz * F
+    parity = {"adjointness_rel_full_size": adj_rel, "e2e_results_reached_host": e2e_ok}
+    if check_small is not None:     # bench.py's checker: the same code path on a graph its CPU oracle finishes in a second
+        parity["small_graph_vs_oracle"] = check_small(make_prop, alloc_of)
+    parity["ok"] = bool(adj_rel < 1e-5 and e2e_ok and (check_small is None or parity["small_graph_vs_oracle"]["rel_fro_max_over_ranks"] < 1e-5))
     return {
+        "parity": parity,
         "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,
         "partition": {"rule": f"block-cyclic relabelling ({stripes} stripes per rank), then contiguous row blocks cut at the non-zero prefix sum", "phases": prop.phases,
                       "transport": prop.transport_name,

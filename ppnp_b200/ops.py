@@ -33,6 +33,7 @@ class NormalizedCSR:
     val32: Optional[torch.Tensor]  # fp32 [nnz]
     dinv: torch.Tensor       # fp32 [n]
     mode: str
+    unit_weights: bool = True  # adj was all ones with an empty diagonal: D_i == number of stored entries of row i of A_hat
 
 
 def csr_normalize(indptr, indices, data=None, mode="sym", want_val64=False, want_val32=True):
@@ -66,31 +67,63 @@ def csr_normalize(indptr, indices, data=None, mode="sym", want_val64=False, want
                                     _lib.ptr(ws), ws_bytes, _lib.current_stream())
     _lib.check(rc, "ppnp_csr_normalize")
     nnz_hat = int(out_indptr[-1].item())
+    # the value-free propagation (csrc/appnp_spmm.cu) takes a row's degree from its edge count: that equals
+    # D = rowsum(adj + I) only for unit weights and a diagonal that was empty (every row gained exactly one entry)
+    unit = data is None and nnz_hat == nnz + n
     return NormalizedCSR(n=n, nnz=nnz_hat, indptr=out_indptr, indices=out_indices[:nnz_hat], deg=out_deg,
                          val64=None if out_val64 is None else out_val64[:nnz_hat],
-                         val32=None if out_val32 is None else out_val32[:nnz_hat], dinv=out_dinv, mode=mode)
+                         val32=None if out_val32 is None else out_val32[:nnz_hat], dinv=out_dinv, mode=mode,
+                         unit_weights=bool(unit))
 
 
 class PropagationGraph:
     """Normalised adjacency + edge-stream plan, ready for ``appnp_propagate``."""
 
     def __init__(self, ahat: NormalizedCSR, chunk_edges=256, order="natural", keep_vals=True, idx16=False, carve=None,
-                 tiled=None):
+                 tiled=None, rows_below=None):
         """order: "natural" | "degree" | a permutation tensor (row-major streams, plan.build_stream_plan) or
         "carve" (hot column blocks first, plan.build_carved_plan; ``carve`` = its keyword arguments).
         idx16: stage the index stream with 16-byte copies from a lane-transposed copy of the stream
         (feature widths 16 and 64; other widths keep the linear stream).
         tiled: keyword arguments of ``tiled.build_tiled_plan`` plus ``slice_width`` (floats of the feature
         dimension per CTA: 16, 32 or 64): rows of high degree run through the shared-memory-resident kernel
-        (csrc/appnp_tiled.cu), the rest through the row-major stream.  Built per feature width on first use."""
+        (csrc/appnp_tiled.cu), the rest through the row-major stream.  Built per feature width on first use.
+        rows_below: rows with fewer stored entries than this go through the one-lane-group-per-row kernel
+        (csrc/appnp_rows.cu) straight off the CSR; the edge stream (or the tiled plan) then holds only the rows of
+        higher degree.  Needs unit weights unless the stored values are kept."""
         self.ahat = ahat
+        self.unit_weights = bool(getattr(ahat, "unit_weights", True))
+        if not self.unit_weights and not keep_vals:
+            raise ValueError("a weighted adjacency (or one with stored diagonal entries) needs the stored values: keep_vals=True")
+        if not self.unit_weights:
+            tiled = None            # the tiled plan's epilogue takes degrees from edge counts as well
         self.tiled_kw = None if tiled is None else dict(tiled)
         self._tiled = {}
         self._keep_vals = bool(keep_vals)
         self._chunk_edges = int(chunk_edges)
         self.mode = ahat.mode
         vals = ahat.val32 if keep_vals else None
-        if isinstance(order, str) and order == "carve":
+        self.rows_part = None       # (rows int32 desc-degree list, RowsPlanStruct) of the low-degree rows
+        self._hub_order = None
+        if rows_below is not None:
+            if isinstance(order, str) and order == "carve":
+                raise ValueError("rows_below goes with the row-major orders")
+            full = degree_order(ahat.indptr)
+            ipl = ahat.indptr.to(torch.int64)
+            n_hub = int(((ipl[1:] - ipl[:-1]) >= int(rows_below)).sum().item())
+            self._hub_order = full[:n_hub]
+            low = full[n_hub:].to(torch.int32).contiguous()
+            if low.numel():
+                rs = _lib.RowsPlanStruct()
+                rs.n, rs.n_rows = ahat.n, int(low.numel())
+                rs.indptr, rs.indices = ahat.indptr.data_ptr(), ahat.indices.data_ptr()
+                rs.vals = vals.data_ptr() if vals is not None else None
+                rs.rows = low.data_ptr()
+                self.rows_part = (low, rs)
+        if self._hub_order is not None:
+            self.plan = (build_stream_plan(ahat.indptr, ahat.indices, vals, chunk_edges, self._hub_order, subset=True)
+                         if self._hub_order.numel() else None)
+        elif isinstance(order, str) and order == "carve":
             self.plan: StreamPlan = build_carved_plan(ahat.indptr, ahat.indices, vals, chunk_edges, **(carve or {}))
         else:
             if carve is not None:
@@ -112,7 +145,7 @@ class PropagationGraph:
 
     def plan_for(self, F):
         """The stream a propagation over F features reads (lane-transposed copy when idx16 applies)."""
-        if not self.idx16 or F not in (16, 64):
+        if self.plan is None or not self.idx16 or F not in (16, 64):
             return self.plan
         G = lane_group_for(F)
         if G not in self._plans16:
@@ -137,19 +170,41 @@ class PropagationGraph:
                 kw["n_ctas"] = max(1, sm.value // (F // W))
             kw.setdefault("slot_rows", (100 * 1024 - 1024 - 128) // (W * 4) - 1)
             kw.setdefault("rest_chunk_edges", self._chunk_edges)
-            tp = build_tiled_plan(self.ahat.indptr, self.ahat.indices, self.ahat.val32 if self._keep_vals else None, **kw)
+            rows_rest = kw.pop("rest", "stream") == "rows"
+            vals = self.ahat.val32 if self._keep_vals else None
+            tp = build_tiled_plan(self.ahat.indptr, self.ahat.indices, vals, build_rest=not rows_rest, **kw)
             rest = tp.rest
             if rest is not None and self.idx16 and F in (16, 64):
                 rest = lane_transpose(rest, lane_group_for(F))
-            self._tiled[F] = (tp, rest, W)
+            rows = None
+            if rows_rest:       # every row the tiled plan does not own goes to the one-group-per-row kernel, by descending degree
+                full = degree_order(self.ahat.indptr)
+                low = full[tp.stats["hub_rows"]:].to(torch.int32).contiguous()
+                if low.numel():
+                    rs = _lib.RowsPlanStruct()
+                    rs.n, rs.n_rows = self.ahat.n, int(low.numel())
+                    rs.indptr, rs.indices = self.ahat.indptr.data_ptr(), self.ahat.indices.data_ptr()
+                    rs.vals = vals.data_ptr() if vals is not None else None
+                    rs.rows = low.data_ptr()
+                    rows = (low, rs)
+            self._tiled[F] = (tp, rest, W, rows)
         return self._tiled[F]
+
+    def parts_for(self, F):
+        """(tiled plan | None, stream plan | None, rows part | None, slice width, partial buffer of the stream part):
+        the kernels a step over F features runs, together producing every row once."""
+        tl = self.tiled_for(F)
+        if tl is not None:
+            tp, rest, W, rows = tl
+            return tp, rest, rows, W, self.rest_partial_buffer(rest, F)
+        return None, self.plan_for(F), self.rows_part, 64, self.partial_buffer(F)
 
     @classmethod
     def from_adjacency(cls, indptr, indices, data=None, mode="sym", **kw):
         return cls(csr_normalize(indptr, indices, data, mode), **kw)
 
     def partial_buffer(self, ld):
-        if self.plan.n_slots == 0:
+        if self.plan is None or self.plan.n_slots == 0:
             return None
         buf = self._partial.get(ld)
         if buf is None:
@@ -175,25 +230,26 @@ def spmm_step(graph: PropagationGraph, Zin, T, alpha, epi=_lib.EPI_PLAIN, use_va
     Zin = Zin.contiguous()
     T = T.contiguous()
     n, F = Zin.shape
+    if not graph.unit_weights and (not use_vals or (int(epi) & 15) != _lib.EPI_PLAIN):
+        raise ValueError("this graph has weights or stored diagonal entries: only the stored-value step (use_vals=True, "
+                         "EPI_PLAIN) is defined for it -- the value-free epilogues take degrees from edge counts")
     if out is None:
         out = torch.empty_like(Zin)
-    tl = graph.tiled_for(F)
-    if tl is not None:
-        tp, rest, W = tl
-        with torch.cuda.device(Zin.device):
-            rc = lib.ppnp_spmm_step_tiled(tp.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), F, F, W, float(alpha), int(epi),
+    tiled, stream_plan, rows, W, partial = graph.parts_for(F)
+    with torch.cuda.device(Zin.device):
+        if tiled is not None:
+            rc = lib.ppnp_spmm_step_tiled(tiled.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), F, F, W, float(alpha), int(epi),
                                           int(bool(use_vals)), _lib.current_stream())
             _lib.check(rc, "ppnp_spmm_step_tiled")
-            if rest is not None:
-                rc = lib.ppnp_spmm_step(rest.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), _lib.ptr(graph.rest_partial_buffer(rest, F)),
-                                        F, F, float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
-                _lib.check(rc, "ppnp_spmm_step")
-        return out
-    partial = graph.partial_buffer(F)
-    with torch.cuda.device(Zin.device):
-        rc = lib.ppnp_spmm_step(graph.plan_for(F).struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), _lib.ptr(partial),
-                                F, F, float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
-    _lib.check(rc, "ppnp_spmm_step")
+        if stream_plan is not None:
+            rc = lib.ppnp_spmm_step(stream_plan.struct(), _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out), _lib.ptr(partial),
+                                    F, F, float(alpha), int(epi), int(bool(use_vals)), _lib.current_stream())
+            _lib.check(rc, "ppnp_spmm_step")
+        if rows is not None:
+            rs = rows[1]
+            rc = lib.ppnp_spmm_step_rows(rs.indptr, rs.indices, rs.vals, rs.rows, rs.n_rows, rs.n, _lib.ptr(Zin), _lib.ptr(T), _lib.ptr(out),
+                                         F, F, float(alpha), int(epi), int(bool(use_vals)), None, None, None, None, 0, _lib.current_stream())
+            _lib.check(rc, "ppnp_spmm_step_rows")
     return out
 
 
@@ -213,16 +269,18 @@ def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False,
         raise ValueError(f"H has {n} rows, graph has {graph.n}")
     if K == 0:
         return H.clone()
+    if not graph.unit_weights:
+        use_vals = True     # edge counts are not degrees here: the value-free form would be silently wrong
     Z = out if out is not None else torch.empty_like(H)
     scratch = scratch if scratch is not None else torch.empty_like(H)
-    tl = graph.tiled_for(F)
-    if tl is not None:
-        tp, rest, W = tl
+    tiled, stream_plan, rows, W, partial = graph.parts_for(F)
+    if tiled is not None or rows is not None:
         with torch.cuda.device(H.device):
-            rc = lib.ppnp_appnp_propagate_tiled(tp.struct(), None if rest is None else rest.struct(), _lib.ptr(H), _lib.ptr(Z),
-                                                _lib.ptr(scratch), _lib.ptr(graph.rest_partial_buffer(rest, F)), F, F, W, int(K),
-                                                float(alpha), MODE[graph.mode], int(bool(use_vals)), _lib.current_stream())
-        _lib.check(rc, "ppnp_appnp_propagate_tiled")
+            rc = lib.ppnp_appnp_propagate_parts(None if tiled is None else tiled.struct(), None if stream_plan is None else stream_plan.struct(),
+                                                None if rows is None else rows[1], _lib.ptr(H), _lib.ptr(Z), _lib.ptr(scratch),
+                                                _lib.ptr(partial), F, F, W, int(K), float(alpha), MODE[graph.mode], int(bool(use_vals)),
+                                                _lib.current_stream())
+        _lib.check(rc, "ppnp_appnp_propagate_parts")
         return Z
     partial = graph.partial_buffer(F)
     with torch.cuda.device(H.device):

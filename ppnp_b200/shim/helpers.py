@@ -19,7 +19,8 @@ Environment switches (main.py has no flag for them and stays unchanged):
                               records the normalised graph for model.PPNP and returns a placeholder
   PPNP_K                      APPNP steps (default 10)
   PPNP_PPR_TOL                stop tolerance of the power iteration building Pi (default 1e-7)
-  PPNP_PPR_METHOD = power | chebyshev   plain fixed point (default) or its Chebyshev acceleration
+  PPNP_PPR_METHOD = chebyshev | power   Chebyshev-accelerated iteration (default: 40 steps instead of 153 at
+                              alpha = 0.1, measured 75 ms against 220 ms at PubMed shape, 9e-8 apart) or the plain fixed point
 """
 import os
 import random
@@ -114,7 +115,7 @@ def compute_ppr(adj, alpha, mode="sym"):
     if os.environ.get("PPNP_MODE", "exact").lower() == "appnp":
         return np.zeros((1, 1), dtype=np.float32)          # placeholder; model.PPNP propagates on the graph
     tol = float(os.environ.get("PPNP_PPR_TOL", "1e-7"))
-    Pi = _P.ppr_dense(ahat, float(alpha), tol=tol, method=os.environ.get("PPNP_PPR_METHOD", "power"))
+    Pi = _P.ppr_dense(ahat, float(alpha), tol=tol, method=os.environ.get("PPNP_PPR_METHOD", "chebyshev"))
     host = torch.empty(Pi.shape, dtype=torch.float32, pin_memory=True)
     host.copy_(Pi)
     torch.cuda.synchronize()

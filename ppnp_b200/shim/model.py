@@ -54,6 +54,7 @@ class _BatchRows:
 
     def __init__(self, owner, idx):
         self.owner, self.idx = owner, idx.to(owner.device)
+        self.support = None      # set by (rows > 0).any(dim=0)
 
     def dense(self):
         return torch.Tensor.__getitem__(self.owner.as_subclass(torch.Tensor), self.idx)
@@ -65,7 +66,10 @@ class _BatchRows:
 
     def __getitem__(self, key):
         if isinstance(key, tuple) and len(key) == 2 and key[0] == slice(None) and torch.is_tensor(key[1]) \
-                and key[1].dtype == torch.bool:
+                and key[1].dtype == torch.bool and key[1] is self.support:
+            # batch-main.py:142 with the mask of :141.  The compact kernels index Hsub by the position of a column
+            # inside THIS mask (colmap = cumsum(sel) - 1, unchecked): any other mask takes the dense path below,
+            # which is valid for arbitrary masks like the reference's ppr_sub[:, mask].
             return _BatchSub(self, key[1])
         return self.dense()[key]
 
@@ -81,7 +85,9 @@ class _BatchRowsPositive:
 
     def any(self, dim=None):
         if dim in (0, -2):
-            return _P.batch_support(self.rows.owner.compact(), self.rows.idx)
+            sel = _P.batch_support(self.rows.owner.compact(), self.rows.idx)
+            self.rows.support = sel          # the one mask the compact product below is valid for
+            return sel
         return (self.rows.dense() > 0).any(dim=dim)
 
     def __getattr__(self, name):

@@ -1,0 +1,85 @@
+"""The drop-in claim end to end (north_star "drops into main.py and batch-main.py unchanged"):
+the reference's OWN scripts, unmodified, run through runpy with [shim, reference] in front of sys.path on a GPU --
+argparse defaults, gen_seeds, `.cuda()` of the pinned Pi, `n_classes` as a 0-d tensor, the CPU-index
+`model.ppr[idx_batch]` path, everything main.py:73-121 / batch-main.py:76-154 does.
+
+Needs a reference checkout next to a GPU: PPNP_REFERENCE, /root/reference, or baseline/_ref/reference (staged by
+tools/stage_reference.sh; git-ignored, travels with the gpurun snapshot).  Skipped when none is reachable."""
+import ast
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "ppnp_b200", "shim")
+
+
+def _reference():
+    for cand in (os.environ.get("PPNP_REFERENCE"), "/root/reference", os.path.join(ROOT, "baseline", "_ref", "reference")):
+        if cand and os.path.isfile(os.path.join(cand, "main.py")) and os.path.isfile(os.path.join(cand, "ppnp", "data", "cora_ml.npz")):
+            return cand
+    return None
+
+
+REF = _reference()
+needs_ref = pytest.mark.skipif(REF is None, reason="no reference checkout reachable (run tools/stage_reference.sh in the build container)")
+
+LAUNCH = ("import sys, runpy; sys.path[:0] = [{shim!r}, {ref!r}, {root!r}]; sys.argv = {argv!r}; "
+          "runpy.run_path({script!r}, run_name='__main__')")
+
+
+def _run(script, extra_argv, env_extra, timeout=900):
+    argv = [script, "--inpath", os.path.join(REF, "ppnp", "data", "cora_ml.npz"), "--n-runs", "1", "--seed", "123", "--verbose"] + extra_argv
+    code = LAUNCH.format(shim=SHIM, ref=REF, root=ROOT, argv=argv, script=os.path.join(REF, script))
+    env = dict(os.environ, **env_extra)
+    env.pop("PYTHONPATH", None)
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=timeout, cwd=REF, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    epochs = [json.loads(l) for l in out.stderr.splitlines() if l.startswith("{") and '"epoch"' in l]
+    records = [ast.literal_eval(l) for l in out.stdout.splitlines() if l.startswith("{") and "'epoch'" in l]
+    assert len(records) == 1, out.stdout[-2000:]
+    return epochs, records[0], out
+
+
+@needs_ref
+@pytest.mark.parametrize("mode,env", [("exact", {}), ("appnp", {"PPNP_MODE": "appnp"}), ("exact-bf16", {"PPNP_GEMM": "bf16"}),
+                                      ("exact-power", {"PPNP_PPR_METHOD": "power"})])
+def test_unchanged_main_py_trains_through_the_shim(mode, env):
+    epochs, record, out = _run("main.py", ["--max-epochs", "40"], dict({"PPNP_MODE": "exact"}, **env))
+    assert len(epochs) == 40 and [e["epoch"] for e in epochs] == list(range(40))
+    assert set(record) == {"epoch", "elapsed", "train_acc", "stop_acc", "valid_acc"}          # main.py:147-153
+    first, last = epochs[0], epochs[-1]
+    assert last["train_acc"] > first["train_acc"] + 0.3 and last["train_acc"] > 0.55          # 7 classes: chance = 0.14
+    assert last["stop_acc"] > 0.4 and last["valid_acc"] > 0.4
+
+
+@needs_ref
+@pytest.mark.parametrize("bs,topk", [(32, 128), (128, 32)])
+def test_unchanged_batch_main_py_trains_through_the_shim(bs, topk):
+    epochs, record, out = _run("batch-main.py", ["--max-epochs", "25", "--batch-size", str(bs), "--ppr-topk", str(topk)], {"PPNP_MODE": "exact"})
+    assert len(epochs) == 25
+    assert {"epoch", "elapsed", "stop_acc", "valid_acc"} <= set(record)
+    assert epochs[-1]["stop_acc"] > epochs[0]["stop_acc"] + 0.15 and epochs[-1]["stop_acc"] > 0.4
+
+
+@needs_ref
+def test_exact_and_appnp_agree_with_the_reference_run_on_cpu():
+    """Same seed, same script: the reference's own modules on the CPU (its stock path, `.cuda()` mapped to identity) and
+    the shim on the GPU must report the same accuracies after a fixed number of epochs up to fp32 / dropout-RNG noise --
+    both runs draw their dropout masks from different generators (CPU vs CUDA), so the comparison is statistical:
+    validation accuracy within 10 points after 60 epochs."""
+    ref_code = ("import sys, runpy, torch; torch.Tensor.cuda = lambda self, *a, **k: self; torch.nn.Module.cuda = lambda self, *a, **k: self; "
+                "sys.path[:0] = [{ref!r}]; sys.argv = {argv!r}; runpy.run_path({script!r}, run_name='__main__')")
+    argv = ["main.py", "--inpath", os.path.join(REF, "ppnp", "data", "cora_ml.npz"), "--n-runs", "1", "--seed", "123", "--max-epochs", "60"]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", ref_code.format(ref=REF, argv=argv, script=os.path.join(REF, "main.py"))],
+                         capture_output=True, text=True, timeout=900, cwd=REF, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    ref_rec = [ast.literal_eval(l) for l in out.stdout.splitlines() if l.startswith("{")][0]
+    _, rec, _ = _run("main.py", ["--max-epochs", "60"], {"PPNP_MODE": "exact"})
+    assert abs(rec["valid_acc"] - ref_rec["valid_acc"]) < 0.10, (rec, ref_rec)
+    assert abs(rec["stop_acc"] - ref_rec["stop_acc"]) < 0.10, (rec, ref_rec)

@@ -407,3 +407,38 @@ def test_argument_errors_are_reported_not_crashes():
     assert P.gather_gemm(Pi, torch.randn(50, 3, device=dev()), torch.zeros(0, dtype=torch.int64, device=dev())).shape == (0, 3)
     # the message of the last failure is retrievable through the C ABI
     assert b"multiple of 8" in _lib.load().ppnp_last_error()
+
+
+def test_appnp_weighted_adjacency_with_diagonal_never_takes_the_value_free_path():
+    """the value-free iteration reads a row's degree off its edge count, which is D only for unit weights and
+    an empty diagonal.  A weighted graph with self loops, large enough for the per-step launches (> 4096 chunks), must give
+    the oracle's result whatever `use_vals` says, and the value-free single step must refuse it."""
+    import ppnp_b200 as P
+    from ppnp_b200 import _lib
+    ip, idx = oracle.rmat_graph(30000, 600000, 15, seed=9)
+    n = len(ip) - 1
+    rng = np.random.RandomState(0)
+    adj = sp.csr_matrix((rng.rand(len(idx)).astype(np.float32) + 0.5, idx, ip), shape=(n, n))
+    adj = (adj + adj.T + sp.diags((rng.rand(n) < 0.3).astype(np.float32) * 2.0)).tocsr().astype(np.float32)
+    adj.sort_indices()
+    ahat = P.csr_normalize(torch.from_numpy(adj.indptr).to(dev()), torch.from_numpy(adj.indices).to(dev()),
+                           torch.from_numpy(adj.data).to(dev()), "sym")
+    assert not ahat.unit_weights
+    g = P.PropagationGraph(ahat, chunk_edges=128, order="degree")
+    assert g.plan.n_chunks > 4096
+    H = rng.randn(n, 16).astype(np.float32)
+    ref = oracle.appnp(oracle.calc_A_hat(adj, "sym"), H.astype(np.float64), 0.1, 10)
+    for uv in (False, True):
+        z = P.appnp_propagate(g, torch.from_numpy(H).to(dev()), 10, 0.1, use_vals=uv).cpu().numpy()
+        assert relerr(z, ref) < 1e-5
+    with pytest.raises(ValueError):
+        P.spmm_step(g, torch.from_numpy(H).to(dev()), torch.from_numpy(H).to(dev()), 0.1, _lib.EPI_Y, False)
+    with pytest.raises(ValueError):
+        P.PropagationGraph(ahat, keep_vals=False)
+    # an all-ones adjacency WITH stored diagonal entries is not "unit" either
+    adj1 = (sp.csr_matrix((np.ones(len(idx), np.float32), idx, ip), shape=(n, n)) + sp.eye(n, format="csr", dtype=np.float32)).tocsr()
+    adj1.sort_indices()
+    a1 = P.csr_normalize(torch.from_numpy(adj1.indptr).to(dev()), torch.from_numpy(adj1.indices).to(dev()), None, "sym")
+    assert not a1.unit_weights
+    z = P.appnp_propagate(P.PropagationGraph(a1, chunk_edges=128), torch.from_numpy(H).to(dev()), 10, 0.1).cpu().numpy()
+    assert relerr(z, oracle.appnp(oracle.calc_A_hat(adj1, "sym"), H.astype(np.float64), 0.1, 10)) < 1e-5

@@ -103,7 +103,7 @@ def test_tiled_rejects_what_it_cannot_run():
     from ppnp_b200 import _lib
     ip, idx, ahat, g = _graph(5000, 60000, 13, 6, tiled=dict(slice_width=32, n_ctas=4, warps_per_cta=4, slot_rows=64, min_hub_degree=8))
     assert g.tiled_for(48) is None          # not a multiple of the slice width: the row-major kernel runs
-    tp, rest, W = g.tiled_for(64)
+    tp, rest, W, _ = g.tiled_for(64)
     lib = _lib.load()
     Z = torch.zeros(ahat.n, 64, device=dev())
     rc = lib.ppnp_spmm_step_tiled(tp.struct(), _lib.ptr(Z), _lib.ptr(Z), _lib.ptr(Z), 64, 64, 32, 0.1, 0, 0, _lib.current_stream())

@@ -65,7 +65,7 @@ def main():
             t0 = time.perf_counter()
             g = g0 if kw is None else P.PropagationGraph(ahat, chunk_edges=256, order="degree", idx16=True, tiled=kw)
             if kw is not None:
-                tp, rest, W = g.tiled_for(F)
+                tp, rest, W, rows = g.tiled_for(F)
                 rec["stats"] = tp.stats
                 rec["rest_edges"] = None if rest is None else rest.nnz
             torch.cuda.synchronize()

@@ -21,7 +21,7 @@ def main():
     ip, idx = rmat_adjacency(n, raw, scale, seed=0, device=dev)
     ahat = P.csr_normalize(ip, idx)
     g = P.PropagationGraph(ahat, chunk_edges=256, order="degree", idx16=True, tiled=kw)
-    tp, rest, W = g.tiled_for(F)
+    tp, rest, W, rows = g.tiled_for(F)
     H = torch.randn(n, F, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
     Z = torch.empty_like(H)
     lib = _lib.load()
