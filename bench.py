@@ -349,16 +349,18 @@ def parity_small_partitioned(make_prop, alloc_of, dev, rank, world, F, K, alpha)
 def sub_bench(argv, gpu_index):
     """Run this script once more in a fresh process on one GPU and return its JSON line (or the error)."""
     import subprocess
-    env = dict(os.environ)
-    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID", "MASTER_PORT"):
-        env.pop(k, None)
+    # a clean single-process environment: everything torch.distributed.run exported to this rank must go (with
+    # TORCHELASTIC_USE_AGENT_STORE left set the child would wait for the parent job's store forever)
+    env = {k: v for k, v in os.environ.items()
+           if not (k.startswith(("TORCHELASTIC_", "GROUP_", "ROLE_", "TORCH_NCCL_", "NCCL_ASYNC")) or
+                   k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "MASTER_PORT", "MASTER_ADDR", "OMP_NUM_THREADS"))}
     env["MASTER_ADDR"] = "127.0.0.1"
     env["MASTER_PORT"] = str(29600 + (os.getpid() % 300))
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     env["CUDA_VISIBLE_DEVICES"] = (vis.split(",")[gpu_index] if vis else str(gpu_index))
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, env=env, stdout=subprocess.PIPE,
-                           stderr=subprocess.PIPE, text=True, timeout=600)
+                           stderr=subprocess.PIPE, text=True, timeout=300)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith("{"):
                 d = json.loads(ln)
@@ -707,7 +709,7 @@ def run_ours(args):
     value = work / (ms * 1e-3)
     bytes_pass = algorithmic_bytes_per_pass(n, nnz, F, value_free=not args.use_vals)
     achieved = bytes_pass / (ms * 1e-3) / 1e9
-    launches_per_pass = 2 * KSTEPS * (2 if graph.plan.n_fix > 0 else 1)
+    launches_per_pass = 2 * KSTEPS * (2 if (graph.plan is not None and graph.plan.n_fix > 0) else 1)
     traffic, traffic_src = measured_traffic(f"{wl}/{args.order}/{'stored-values' if args.use_vals else 'value-free'}")
 
     # ---- e2e: host buffers through the public API, copies inside the timed region

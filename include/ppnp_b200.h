@@ -31,13 +31,18 @@ extern "C" {
 /* normalisation modes of helpers.py:58-66 calc_A_hat(adj, mode) */
 #define PPNP_MODE_SYM 0    /* D^-1/2 (A+I) D^-1/2   helpers.py:61-63 */
 #define PPNP_MODE_RW 1     /* D^-1 (A+I)            helpers.py:64-66 */
+/* 'sym' with the input ALREADY scaled, H_in = D^-1/2 H (the fused encoder tail, ppnp_linear_rowscale, writes it
+ * that way): every step is value-free, the stored values of A_hat are never read and need not exist. */
+#define PPNP_MODE_SYM_Y0 2
 
 /* epilogue of one propagation step, out[r] = a(deg_r) * acc_r + b(deg_r) * T[r] */
 #define PPNP_EPI_PLAIN 0   /* a = 1-alpha,            b = alpha            stored values, Z-space         */
 #define PPNP_EPI_Z2Y 1     /* a = (1-alpha)/sqrt(d),  b = alpha/sqrt(d)    stored values, first step Z->Y  */
 #define PPNP_EPI_Y 2       /* a = (1-alpha)/d,        b = alpha/sqrt(d)    value-free, Y = D^-1/2 Z space  */
 #define PPNP_EPI_Y2Z 3     /* a = (1-alpha)/sqrt(d),  b = alpha            value-free, last step Y->Z      */
-#define PPNP_EPI_RW 4      /* a = (1-alpha)/d,        b = alpha            value-free 'rw' mode            */
+#define PPNP_EPI_RW 4      /* a = (1-alpha)/d,        b = alpha            value-free 'rw' mode; also the inner steps of
+                              PPNP_MODE_SYM_Y0 (T = Y0 = D^-1/2 H)                                      */
+#define PPNP_EPI_Y02Z 5    /* a = (1-alpha)/sqrt(d),  b = alpha*sqrt(d)    last step of PPNP_MODE_SYM_Y0, T = Y0      */
 /* OR-ed onto one of the above: out[r] = a * acc_r + 1 * T[r] with T == Zout, i.e. the step ADDS its
  * contribution to rows an earlier pass already wrote (multi-pass steps of the partitioned form,
  * ppnp_b200/dist.py: local columns first, halo columns once they have arrived). */
@@ -240,6 +245,25 @@ int ppnp_appnp_propagate_parts(const ppnp_tiled_plan_t* tiled, const ppnp_plan_t
                                const ppnp_rows_plan_t* rows, const float* H, float* Z, float* scratch,
                                float* partial, int64_t ld, int32_t F, int32_t slice_width, int32_t K,
                                float alpha, int32_t mode, int32_t use_vals, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2d) Encoder tail fused with the row scaling of the propagation.
+ *      replaces model.py:51 (the encoder's last nn.Linear) where it feeds model.py:63 in APPNP mode:
+ *        out[i, :] = scale_i * (A[i, :] @ W^T + bias)     A: n x hidden row-major (contiguous), W: C x hidden
+ *      (nn.Linear weight layout), bias / scale nullable.  With scale = D^-1/2 (ppnp_csr_normalize's out_dinv) the
+ *      result is Y0 = D^-1/2 H: ppnp_appnp_propagate(..., mode = PPNP_MODE_SYM_Y0) propagates it value-free in
+ *      every step and returns Z = P_K(A_hat) H without H or the stored values of A_hat ever existing.
+ *      backward: dA = scale * (dOut @ W) (nullable), dW = sum_i scale_i dOut_i^T A_i, dbias (nullable);
+ *      two-stage fixed-order reduction (deterministic); workspace from the _workspace_bytes query.
+ *      hidden <= 256, C <= 64.
+ * ---------------------------------------------------------------------------------------- */
+int ppnp_linear_rowscale(const float* A, int64_t n, int32_t hidden, const float* W, const float* bias,
+                         const float* scale, float* out, int64_t ld_out, int32_t C, void* stream);
+int64_t ppnp_linear_rowscale_backward_workspace_bytes(int64_t n, int32_t hidden, int32_t C);
+int ppnp_linear_rowscale_backward(const float* A, const float* dOut, int64_t ld_dout, int64_t n,
+                                  int32_t hidden, int32_t C, const float* W, const float* scale,
+                                  float* dA, float* dW, float* dbias, void* workspace,
+                                  int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (3) Exact PPNP.                                      replaces helpers.py:68-71 compute_ppr

@@ -12,8 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PPNP_B200_LIB") or os.path.join(_HERE, "libppnp_b200.so")
 
 # epilogues / modes (keep in sync with include/ppnp_b200.h)
-MODE_SYM, MODE_RW = 0, 1
-EPI_PLAIN, EPI_Z2Y, EPI_Y, EPI_Y2Z, EPI_RW = 0, 1, 2, 3, 4
+MODE_SYM, MODE_RW, MODE_SYM_Y0 = 0, 1, 2
+EPI_PLAIN, EPI_Z2Y, EPI_Y, EPI_Y2Z, EPI_RW, EPI_Y02Z = 0, 1, 2, 3, 4, 5
 EPI_ACC = 16
 EPI_INPLACE = 32
 STD_UNDIRECTED, STD_NO_SELF_LOOPS, STD_LCC = 1, 2, 4
@@ -64,6 +64,9 @@ SIGNATURES = {
     "ppnp_spmm_step_rows": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _i32, _f32, _i32, _i32, _p, _p, _p, _p, _i32, _p]),
     "ppnp_appnp_propagate_parts": (C.c_int, [C.POINTER(TiledPlanStruct), C.POINTER(PlanStruct), C.POINTER(RowsPlanStruct), _p, _p, _p, _p,
                                              _i64, _i32, _i32, _i32, _f32, _i32, _i32, _p]),
+    "ppnp_linear_rowscale": (C.c_int, [_p, _i64, _i32, _p, _p, _p, _p, _i64, _i32, _p]),
+    "ppnp_linear_rowscale_backward_workspace_bytes": (_i64, [_i64, _i32, _i32]),
+    "ppnp_linear_rowscale_backward": (C.c_int, [_p, _p, _i64, _i64, _i32, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "ppnp_ppr_dense": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),
     "ppnp_ppr_dense_cheb": (C.c_int, [_p, _p, _p, _i64, _f32, _i32, _p, _p, _p]),
     "ppnp_gather_gemm_f32": (C.c_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _i32, _p, _i64, _i32, _p]),

@@ -145,7 +145,7 @@ int ppnp_spmm_step_rows(const int32_t* indptr, const int32_t* indices, const flo
     PPNP_REQUIRE(Zin && T && Zout && Zin != Zout, "null or aliased matrix pointer");
     PPNP_REQUIRE(F > 0 && F % 4 == 0 && ld >= F && ld % 4 == 0 && ld < ((int64_t)1 << 30), "need F % 4 == 0, F <= ld < 2^30, ld % 4 == 0");
     PPNP_REQUIRE(aligned16(Zin) && aligned16(T) && aligned16(Zout), "matrices must be 16-byte aligned");
-    PPNP_REQUIRE(epi >= PPNP_EPI_PLAIN && epi <= PPNP_EPI_RW, "bad epilogue");
+    PPNP_REQUIRE(epi >= PPNP_EPI_PLAIN && epi <= PPNP_EPI_Y02Z, "bad epilogue");
     PPNP_REQUIRE(!use_vals || vals != nullptr, "use_vals needs the stored values");
     PPNP_REQUIRE(push_ptr == nullptr || (push_code && push_first && peer_bases_host && n_peers >= 1 && n_peers <= PPNP_MAX_PEERS),
                  "push lists need codes, the per-row summary and 1..PPNP_MAX_PEERS peer base pointers");
@@ -178,17 +178,12 @@ extern "C" int ppnp_appnp_propagate_parts(const ppnp_tiled_plan_t* tiled, const 
     PPNP_REQUIRE(tiled || stream_plan || rows, "at least one part is required");
     PPNP_REQUIRE(H && Z && scratch && H != Z && H != scratch && Z != scratch, "H, Z, scratch must be distinct buffers");
     PPNP_REQUIRE(K >= 1, "K >= 1");
-    PPNP_REQUIRE(mode == PPNP_MODE_SYM || mode == PPNP_MODE_RW, "bad mode");
+    PPNP_REQUIRE(mode == PPNP_MODE_SYM || mode == PPNP_MODE_RW || mode == PPNP_MODE_SYM_Y0, "bad mode");
     const float* src = H;
     for (int k = 1; k <= K; ++k) {
         float* dst = ((K - k) % 2 == 0) ? Z : scratch;
         int epi, vals;
-        if (use_vals) { epi = PPNP_EPI_PLAIN; vals = 1; }
-        else if (mode == PPNP_MODE_RW) { epi = PPNP_EPI_RW; vals = 0; }
-        else if (K == 1) { epi = PPNP_EPI_PLAIN; vals = 1; }
-        else if (k == 1) { epi = PPNP_EPI_Z2Y; vals = 1; }
-        else if (k == K) { epi = PPNP_EPI_Y2Z; vals = 0; }
-        else { epi = PPNP_EPI_Y; vals = 0; }
+        step_form(mode, use_vals, k, K, epi, vals);
         int rc;
         if (tiled) {
             rc = ppnp_spmm_step_tiled(tiled, src, H, dst, ld, F, slice_width, alpha, epi, vals, stream);

@@ -805,7 +805,7 @@ int ppnp_spmm_step(const ppnp_plan_t* plan, const float* Zin, const float* T, fl
     PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
-    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~63) == 0, "bad epilogue");
+    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_Y02Z && (epi & ~63) == 0, "bad epilogue");
     PPNP_REQUIRE(!(epi & PPNP_EPI_ACC) || T == Zout, "PPNP_EPI_ACC adds to the output: pass T == Zout");
     PPNP_REQUIRE(!(epi & PPNP_EPI_INPLACE) || (epi & PPNP_EPI_ACC), "PPNP_EPI_INPLACE goes with PPNP_EPI_ACC");
     PushArgs none{};
@@ -823,28 +823,23 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
     PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(K >= 1, "K >= 1");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
-    PPNP_REQUIRE(mode == PPNP_MODE_SYM || mode == PPNP_MODE_RW, "bad mode");
+    PPNP_REQUIRE(mode == PPNP_MODE_SYM || mode == PPNP_MODE_RW || mode == PPNP_MODE_SYM_Y0, "bad mode");
+    PPNP_REQUIRE(mode != PPNP_MODE_SYM_Y0 || !use_vals, "PPNP_MODE_SYM_Y0 is value-free");
     PPNP_REQUIRE(!(use_vals || (mode == PPNP_MODE_SYM)) || plan->vals != nullptr,
                  "plan->vals required (stored-value steps / first 'sym' step)");
     cudaStream_t stream = as_stream(stream_);
     // small graphs: all K steps in one cooperative launch (grid barriers instead of 2K launches)
-    if (K >= 2 && plan->vals != nullptr && plan->row_deg == nullptr && plan->n_chunks <= PPNP_PERSISTENT_MAX_CHUNKS &&
+    if (K >= 2 && mode != PPNP_MODE_SYM_Y0 && plan->vals != nullptr && plan->row_deg == nullptr && plan->n_chunks <= PPNP_PERSISTENT_MAX_CHUNKS &&
         PPNP_PLAN_LANE_GROUP(plan->flags) == 0 && persistent_enabled()) {
         return dispatch_persistent(plan, H, Z, scratch, partial, ld, F, K, alpha, stream);
     }
     const float* src = H;
     for (int k = 1; k <= K; ++k) {
         float* dst = ((K - k) % 2 == 0) ? Z : scratch;
-        int epi;
-        bool vals;
-        if (use_vals) { epi = PPNP_EPI_PLAIN; vals = true; }
-        else if (mode == PPNP_MODE_RW) { epi = PPNP_EPI_RW; vals = false; }
-        else if (K == 1) { epi = PPNP_EPI_PLAIN; vals = true; }
-        else if (k == 1) { epi = PPNP_EPI_Z2Y; vals = true; }
-        else if (k == K) { epi = PPNP_EPI_Y2Z; vals = false; }
-        else { epi = PPNP_EPI_Y; vals = false; }
+        int epi, vals;
+        step_form(mode, use_vals, k, K, epi, vals);
         PushArgs none{};
-        rc = dispatch_step(plan, src, H, dst, partial, ld, F, alpha, epi, vals, none, stream);
+        rc = dispatch_step(plan, src, H, dst, partial, ld, F, alpha, epi, vals != 0, none, stream);
         if (rc) return rc;
         src = dst;
     }
@@ -863,7 +858,7 @@ int ppnp_spmm_step_push(const ppnp_plan_t* plan, const float* Zin, const float* 
     PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
-    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_RW && (epi & ~63) == 0, "bad epilogue");
+    PPNP_REQUIRE((epi & 15) >= PPNP_EPI_PLAIN && (epi & 15) <= PPNP_EPI_Y02Z && (epi & ~63) == 0, "bad epilogue");
     PPNP_REQUIRE(push_ptr == nullptr || (push_code && push_first && peer_bases_host && n_peers >= 1 && n_peers <= PPNP_MAX_PEERS),
                  "push lists need codes, the per-row summary and 1..PPNP_MAX_PEERS peer base pointers");
     PushArgs pa{};

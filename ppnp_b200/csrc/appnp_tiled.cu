@@ -294,7 +294,7 @@ int ppnp_spmm_step_tiled(const ppnp_tiled_plan_t* plan, const float* Zin, const 
     PPNP_REQUIRE(Zin && T && Zout && Zin != Zout, "null or aliased matrix pointer");
     PPNP_REQUIRE(F > 0 && ld >= F && ld % 4 == 0 && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30, ld % 4 == 0");
     PPNP_REQUIRE(aligned16(Zin) && aligned16(T) && aligned16(Zout), "matrices must be 16-byte aligned");
-    PPNP_REQUIRE(epi >= PPNP_EPI_PLAIN && epi <= PPNP_EPI_RW, "bad epilogue");
+    PPNP_REQUIRE(epi >= PPNP_EPI_PLAIN && epi <= PPNP_EPI_Y02Z, "bad epilogue");
     PPNP_REQUIRE(!use_vals || plan->vals != nullptr, "use_vals needs plan->vals");
     cudaStream_t stream = as_stream(stream_);
 #define PPNP_TGO(G_) return use_vals ? launch_tiled<G_, true>(plan, Zin, T, Zout, ld, F, alpha, epi, stream) \

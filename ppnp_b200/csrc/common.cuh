@@ -97,8 +97,20 @@ __device__ __forceinline__ void epi_coef(int epi, float alpha, float deg, float&
         case PPNP_EPI_Y: a = oma * __frcp_rn(deg); b = alpha * rsqrtf(deg); break;
         case PPNP_EPI_Y2Z: a = oma * rsqrtf(deg); b = alpha; break;
         case PPNP_EPI_RW: a = oma * __frcp_rn(deg); b = alpha; break;
+        case PPNP_EPI_Y02Z: a = oma * rsqrtf(deg); b = alpha * sqrtf(deg); break;
     }
     if (epi & PPNP_EPI_ACC) b = 1.0f;   // T is the output itself: add to what an earlier pass wrote
+}
+
+// Epilogue and value use of step k of K (1-based) of a propagation, shared by every K-step entry point.
+inline void step_form(int mode, int use_vals, int k, int K, int& epi, int& vals) {
+    if (mode == PPNP_MODE_SYM_Y0) { epi = (k == K) ? PPNP_EPI_Y02Z : PPNP_EPI_RW; vals = 0; }
+    else if (use_vals) { epi = PPNP_EPI_PLAIN; vals = 1; }
+    else if (mode == PPNP_MODE_RW) { epi = PPNP_EPI_RW; vals = 0; }
+    else if (K == 1) { epi = PPNP_EPI_PLAIN; vals = 1; }
+    else if (k == 1) { epi = PPNP_EPI_Z2Y; vals = 1; }
+    else if (k == K) { epi = PPNP_EPI_Y2Z; vals = 0; }
+    else { epi = PPNP_EPI_Y; vals = 0; }
 }
 
 }  // namespace ppnp

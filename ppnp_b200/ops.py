@@ -253,11 +253,13 @@ def spmm_step(graph: PropagationGraph, Zin, T, alpha, epi=_lib.EPI_PLAIN, use_va
     return out
 
 
-def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False, out=None, scratch=None):
+def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False, out=None, scratch=None, scaled_input=False):
     """K steps of Z <- (1-alpha) A_hat Z + alpha H from Z_0 = H (north_star; forward and backward).
 
     ``use_vals=False`` runs the value-free Y-space iteration (stored values only in step 1),
     ``use_vals=True`` multiplies by the stored A_hat values in every step.
+    ``scaled_input=True``: ``H`` holds D^-1/2 H already (``linear_rowscale`` writes it that way): every step is
+    value-free, the stored values are never read (PPNP_MODE_SYM_Y0); the result is the same Z.
     """
     lib = _lib.load()
     _require_cuda(H)
@@ -269,8 +271,11 @@ def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False,
         raise ValueError(f"H has {n} rows, graph has {graph.n}")
     if K == 0:
         return H.clone()
+    if scaled_input and (graph.mode != "sym" or not graph.unit_weights or use_vals):
+        raise ValueError("scaled_input is the value-free 'sym' iteration on a unit-weight graph")
     if not graph.unit_weights:
         use_vals = True     # edge counts are not degrees here: the value-free form would be silently wrong
+    mode_code = _lib.MODE_SYM_Y0 if scaled_input else MODE[graph.mode]
     Z = out if out is not None else torch.empty_like(H)
     scratch = scratch if scratch is not None else torch.empty_like(H)
     tiled, stream_plan, rows, W, partial = graph.parts_for(F)
@@ -278,14 +283,14 @@ def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False,
         with torch.cuda.device(H.device):
             rc = lib.ppnp_appnp_propagate_parts(None if tiled is None else tiled.struct(), None if stream_plan is None else stream_plan.struct(),
                                                 None if rows is None else rows[1], _lib.ptr(H), _lib.ptr(Z), _lib.ptr(scratch),
-                                                _lib.ptr(partial), F, F, W, int(K), float(alpha), MODE[graph.mode], int(bool(use_vals)),
+                                                _lib.ptr(partial), F, F, W, int(K), float(alpha), mode_code, int(bool(use_vals)),
                                                 _lib.current_stream())
         _lib.check(rc, "ppnp_appnp_propagate_parts")
         return Z
     partial = graph.partial_buffer(F)
     with torch.cuda.device(H.device):
         rc = lib.ppnp_appnp_propagate(graph.plan_for(F).struct(), _lib.ptr(H), _lib.ptr(Z), _lib.ptr(scratch),
-                                      _lib.ptr(partial), F, F, int(K), float(alpha), MODE[graph.mode],
+                                      _lib.ptr(partial), F, F, int(K), float(alpha), mode_code,
                                       int(bool(use_vals)), _lib.current_stream())
     _lib.check(rc, "ppnp_appnp_propagate")
     return Z
@@ -325,6 +330,79 @@ class _APPNPFunction(torch.autograd.Function):
 def appnp(H, graph, K=10, alpha=0.1, use_vals=False):
     """Differentiable APPNP propagation."""
     return _APPNPFunction.apply(H, graph, K, alpha, use_vals)
+
+
+# ------------------------------------------------------------------------------ fused encoder tail (SURVEY 8f rank 2)
+def linear_rowscale(A, W, bias=None, scale=None):
+    """``scale[:, None] * (A @ W.T + bias)`` (csrc/encoder_tail.cu): model.py:51's last linear with the row scaling of
+    the propagation fused in.  A: [n, hidden] fp32, W: [C, hidden] (nn.Linear layout)."""
+    lib = _lib.load()
+    _require_cuda(A, W, bias, scale)
+    A, W = A.contiguous(), W.contiguous()
+    n, hidden = A.shape
+    C = W.shape[0]
+    if W.shape[1] != hidden:
+        raise ValueError("W must be [C, hidden]")
+    out = torch.empty((n, C), dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.ppnp_linear_rowscale(_lib.ptr(A), n, hidden, _lib.ptr(W), _lib.ptr(None if bias is None else bias.contiguous()),
+                                      _lib.ptr(None if scale is None else scale.contiguous()), _lib.ptr(out), C, C, _lib.current_stream())
+    _lib.check(rc, "ppnp_linear_rowscale")
+    return out
+
+
+def linear_rowscale_backward(A, dOut, W, scale=None, need_dA=True, need_dbias=False):
+    """Adjoint of ``linear_rowscale``: (dA, dW, dbias)."""
+    lib = _lib.load()
+    _require_cuda(A, dOut, W, scale)
+    A, W, dOut = A.contiguous(), W.contiguous(), dOut.contiguous()
+    n, hidden = A.shape
+    C = W.shape[0]
+    dA = torch.empty_like(A) if need_dA else None
+    dW = torch.empty_like(W)
+    dbias = torch.empty(C, dtype=torch.float32, device=A.device) if need_dbias else None
+    ws_bytes = lib.ppnp_linear_rowscale_backward_workspace_bytes(n, hidden, C)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=A.device)
+    with torch.cuda.device(A.device):
+        rc = lib.ppnp_linear_rowscale_backward(_lib.ptr(A), _lib.ptr(dOut), C, n, hidden, C, _lib.ptr(W),
+                                               _lib.ptr(None if scale is None else scale.contiguous()), _lib.ptr(dA), _lib.ptr(dW),
+                                               _lib.ptr(dbias), _lib.ptr(ws), ws_bytes, _lib.current_stream())
+    _lib.check(rc, "ppnp_linear_rowscale_backward")
+    return dA, dW, dbias
+
+
+class _FusedTailAPPNP(torch.autograd.Function):
+    """Z = P_K(A_hat) (A1 @ W^T + b) without H: the last linear writes Y0 = D^-1/2 H, the K steps run value-free
+    (PPNP_MODE_SYM_Y0).  Backward: P_K is symmetric, so dH = P_K(dZ) = D^1/2 P_Y(D^-1/2 dZ) through the same two
+    kernels -- the scaling of dZ rides in the adjoint of the linear layer."""
+
+    @staticmethod
+    def forward(ctx, A1, W, bias, graph, K, alpha):
+        dinv = graph.ahat.dinv
+        Y0 = linear_rowscale(A1, W, bias, dinv)
+        Z = appnp_propagate(graph, Y0, K, alpha, scaled_input=True)
+        ctx.save_for_backward(A1, W)
+        ctx.graph, ctx.K, ctx.alpha, ctx.has_bias = graph, K, alpha, bias is not None
+        return Z
+
+    @staticmethod
+    def backward(ctx, gZ):
+        A1, W = ctx.saved_tensors
+        g = ctx.graph
+        dinv = g.ahat.dinv
+        # dH = P(gZ): scale gZ by D^-1/2 (elementwise, n x C), propagate value-free
+        G0 = gZ.contiguous() * dinv[:, None]
+        dH = appnp_propagate(g, G0, ctx.K, ctx.alpha, scaled_input=True)
+        dA, dW, db = linear_rowscale_backward(A1, dH, W, None, need_dA=ctx.needs_input_grad[0], need_dbias=ctx.has_bias)
+        return dA, dW, db, None, None, None
+
+
+def appnp_fused_tail(A1, W, bias, graph, K=10, alpha=0.1):
+    """Differentiable ``appnp(A1 @ W.T + bias, graph)`` with the encoder's last linear fused into the propagation's
+    input scaling (no H, no stored A_hat values)."""
+    if graph.mode != "sym" or not graph.unit_weights:
+        raise ValueError("the fused tail is the value-free 'sym' iteration on a unit-weight graph")
+    return _FusedTailAPPNP.apply(A1, W, bias, graph, K, alpha)
 
 
 # ------------------------------------------------------------------------------ exact PPNP

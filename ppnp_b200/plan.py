@@ -315,7 +315,7 @@ def build_carved_plan(indptr, indices, vals=None, chunk_edges=256, block_cols=51
     not the row count (a shard of the partitioned form: local rows x [local | halo] columns); columns are
     ranked by how many stored entries reference them -- for the symmetric A_hat that IS the row degree.
     With blocks sized for the L2 instead of the L1 (e.g. 16 blocks of n/16 columns) the same stream keeps the
-    cold gathers of the hub rows inside an L2-resident window (oracle/l1sim.c with one cache models it).
+    cold gathers of the hub rows inside an L2-resident window (tools/l1sim.c with one cache models it).
     ``levels`` = [(block_cols, n_blocks, min_piece), ...] stacks several block sizes along the rank axis
     (e.g. 64 L1-sized blocks over the hottest columns, then L2-sized blocks over the rest) and replaces
     the three scalar parameters.

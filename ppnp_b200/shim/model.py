@@ -156,6 +156,10 @@ class PPNP(nn.Module):
         # full-batch branch (model.py:63); main.py still hands over the dense tensor, its CSR is built once
         self._sparse_x = os.environ.get("PPNP_SPARSE_X", "0") == "1"
         self._sx, self._sx_key = None, None
+        # PPNP_FUSED_TAIL=1 (APPNP mode): the encoder's last linear (model.py:51) writes D^-1/2 H straight from the hidden
+        # activations and the K steps run value-free from the first one (ppnp_b200.appnp_fused_tail): H is never
+        # materialised and the stored values of A_hat are never read
+        self._fused_tail = os.environ.get("PPNP_FUSED_TAIL", "0") == "1"
         if self.mode == "appnp":
             import helpers as _h            # the shim module that recorded the graph (helpers.compute_ppr)
             if _h.LAST_GRAPH["ahat"] is None:
@@ -193,6 +197,10 @@ class PPNP(nn.Module):
 
     def forward(self, X, idx=None, ppr=None):
         if idx is not None:
+            if self.mode == "appnp" and self._fused_tail and not self._sparse_x and self._graph.unit_weights:
+                A1 = self.encoder[3](self.encoder[2](self.encoder[1](self.encoder[0](X))))       # model.py:47-50
+                last = self.encoder[4]
+                return _P.appnp_fused_tail(A1, last.weight, last.bias, self._graph, self.K, self._alpha)[idx]
             H = self._encode_full(X)
             if self.mode == "appnp":
                 return _P.appnp(H, self._graph, self.K, self._alpha)[idx]

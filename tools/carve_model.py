@@ -1,7 +1,7 @@
 """DESIGN TOOL (not product code): rank carved-stream parameters on the CPU before spending GPU time.
 
 Builds the config-4 R-MAT graph with the oracle's generator, the edge streams with ppnp_b200/plan.py (torch
-on the CPU) and feeds their column stream to the LRU model oracle/l1sim.c:
+on the CPU) and feeds their column stream to the LRU model tools/l1sim.c:
 
   python tools/carve_model.py l1     per-SM L1 (148 SMs, units of 64 chunks): rows crossing L2 -> SM
   python tools/carve_model.py l2     one shared cache: rows crossing HBM -> L2, for 256-byte rows (config 4,
@@ -25,7 +25,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ppnp_oracle as oracle  # noqa: E402
 from ppnp_b200.plan import build_carved_plan, build_stream_plan, degree_order  # noqa: E402
 
-SIM = os.path.join(ROOT, "oracle", "_build", "l1sim")
+SIM = os.path.join(ROOT, "tools", "_build", "l1sim")
 
 
 def misses(plan, cache_rows, sms, unit, l2_rows=0):
@@ -39,7 +39,7 @@ def misses(plan, cache_rows, sms, unit, l2_rows=0):
 
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "l1"
-    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "_build/l1sim"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tools"), "_build/l1sim"], check=True, capture_output=True)
     ip, idx = oracle.rmat_graph(2_000_000, 26_400_000, 21)
     oip, oidx, _, _ = oracle.c_a_hat(ip, idx, None, "sym")
     tip, tidx = torch.from_numpy(oip.astype(np.int32)), torch.from_numpy(oidx)
