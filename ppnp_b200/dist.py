@@ -440,6 +440,8 @@ class PartitionedPropagation:
         from . import _lib
         t = self.topo
         cur = torch.cuda.current_stream() if self.on_gpu else None
+        if t.world > 1 and self.on_gpu:
+            rank_barrier(None, H_ext.device, getattr(self, "group", None))     # entry barrier: peers' buffers are ready
         src = H_ext
         for k in range(1, K + 1):
             dst = Z_ext if (K - k) % 2 == 0 else S_ext
@@ -627,6 +629,8 @@ class PipelinedPushPropagation:
         multi = t.world > 1
         cur = torch.cuda.current_stream() if self.on_gpu else None
         ready = None
+        if multi and self.on_gpu:
+            rank_barrier(None, H_ext.device, getattr(self, "group", None))     # entry barrier: peers' buffers are ready
         if multi:                                              # halo of the input for step 1
             if self.on_gpu:
                 self.comm_stream.wait_stream(cur)
@@ -688,11 +692,18 @@ class FusedPushPropagation:
     MAX_PEERS = 8
 
     def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, group=None, step_fn=None, carve=None,
-                 idx16=False):
+                 idx16=False, rows_below=None, rows_order="dest"):
         """carve: keyword arguments of plan.build_carved_plan (block_cols, n_blocks, min_piece): stream the
         shard with its hot column blocks first (blocks sized for the L2: the cold gathers of the hub rows
         stay inside an L2-resident window) instead of in plain degree order.
-        idx16: 16-byte staging of a lane-transposed copy of the stream (feature widths 16 and 64), as on one GPU."""
+        idx16: 16-byte staging of a lane-transposed copy of the stream (feature widths 16 and 64), as on one GPU.
+        rows_below: rows of the shard with fewer stored entries go through the one-lane-group-per-row kernel
+        (csrc/appnp_rows.cu, same fused push in its epilogue), the stream keeps the rows of higher degree.
+        rows_order = "dest": those rows are processed grouped by the peer that wants them and, inside a peer, in the
+        order of their halo slots there, so that the rows a warp finishes together land in CONSECUTIVE slots of one
+        peer: one 64 * GPW-byte contiguous NVLink write per warp store instead of GPW scattered 64-byte ones
+        (measured: 64-byte peer writes move at ~490 GB/s, profiles/r01_scaling.md).  "degree": descending degree
+        (equal trip counts inside a warp), as on one GPU."""
         import ctypes as C
         from .plan import build_carved_plan, build_stream_plan
         self.topo, self.group, self._step_fn = topo, group, step_fn
@@ -708,12 +719,21 @@ class FusedPushPropagation:
         row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), deg)
         vals = dinv_ext[row_of] * dinv_ext[topo.indices.to(torch.int64)]
         del row_of
+        self.rows_part = None
+        self._rows_below, self._rows_order = rows_below, rows_order
         if carve:
             plan = build_carved_plan(ip, topo.indices, vals, chunk_edges, n_cols=n_local + topo.n_halo, wide_cta=False,
                                      **carve)
         else:
             order = torch.sort(deg, descending=True, stable=True).indices
-            plan = build_stream_plan(ip, topo.indices, vals, chunk_edges, order)
+            if rows_below is not None and step_fn is None and self.on_gpu:
+                n_hub = int((deg >= int(rows_below)).sum().item())
+                self._low_rows = order[n_hub:]                     # ordered for good below, once the push lists exist
+                self._csr = (ip.to(torch.int32).contiguous(), topo.indices.to(torch.int32).contiguous(), vals.contiguous())
+                order = order[:n_hub]
+                plan = build_stream_plan(ip, topo.indices, vals, chunk_edges, order, subset=True) if n_hub else None
+            else:
+                plan = build_stream_plan(ip, topo.indices, vals, chunk_edges, order)
         self.sub = _SubGraph(plan, step_fn)
         self.plans = [self.sub]
         self.idx16, self._plans16 = bool(idx16) and step_fn is None, {}
@@ -759,9 +779,23 @@ class FusedPushPropagation:
             first[one] = codes[start[one]]
             first[cnt > 1] = -2
         self.push_first = first.to(torch.int32).contiguous()
+        if getattr(self, "_low_rows", None) is not None and self._low_rows.numel():
+            low = self._low_rows
+            if rows_order == "dest":
+                # key = (peer of the first destination, slot there); rows nobody wants go last, by descending degree
+                if codes.numel():
+                    c0 = codes[pp[:-1][low].clamp(max=int(codes.numel()) - 1)]
+                    key = torch.where(cnt[low] > 0, c0, torch.full_like(c0, 1 << 40))
+                    low = low[torch.sort(key, stable=True).indices]
+            rs = _lib_mod().RowsPlanStruct()
+            rs.n, rs.n_rows = n_local, int(low.numel())
+            self._low_rows_i32 = low.to(torch.int32).contiguous()
+            rs.indptr, rs.indices, rs.vals = self._csr[0].data_ptr(), self._csr[1].data_ptr(), self._csr[2].data_ptr()
+            rs.rows = self._low_rows_i32.data_ptr()
+            self.rows_part = rs
         self.handles, self._bases = {}, {}
         self._C = C
-        self.transport_name = "fused-push" if self.on_gpu else "fused-p2p"
+        self.transport_name = ("fused-push" if self.on_gpu else "fused-p2p") + ("" if self.rows_part is None else f"+rows<{rows_below}/{rows_order}")
         self.phases, self.rounds = "one kernel per step, push in the epilogue", []
 
     def alloc(self, F, count=3):
@@ -848,6 +882,16 @@ class FusedPushPropagation:
         lib = _lib.load()
         F = src.shape[1]
         plan = self.sub.plan
+        if self.rows_part is not None:
+            rs = self.rows_part
+            rc = lib.ppnp_spmm_step_rows(rs.indptr, rs.indices, rs.vals, rs.rows, rs.n_rows, rs.n, _lib.ptr(src), _lib.ptr(T), _lib.ptr(dst),
+                                         F, F, float(alpha), int(epi), int(bool(use_vals)),
+                                         _lib.ptr(self.push_ptr) if push else None, _lib.ptr(self.push_code) if push else None,
+                                         _lib.ptr(self.push_first) if push else None, self._bases[dst.data_ptr()] if push else None,
+                                         self.topo.world if push else 0, _lib.current_stream())
+            _lib.check(rc, "ppnp_spmm_step_rows")
+            if plan is None:
+                return
         if self.idx16 and F in (16, 64):
             from .plan import lane_group_for, lane_transpose
             G = lane_group_for(F)
@@ -876,11 +920,10 @@ class FusedPushPropagation:
         t = self.topo
         multi = t.world > 1
         if multi:
-            if K == 1:
-                # the only step of a K = 1 call reads the halo of its INPUT; with K >= 2 the last step reads the
-                # halo of the previous iterate, so a peer that has already started its next call (and pushes that
-                # call's input) cannot overwrite rows this rank still gathers.  For K = 1 order the calls explicitly.
-                self._barrier(H_ext)
+            # entry barrier: a peer that is ahead must not push this call's input halo into my buffers while I am
+            # still initialising them (the caller zeroes / fills H_ext right before the call) or, for K = 1, while
+            # the previous call's only step still gathers the halo of ITS input.  One 4-byte all-reduce per call.
+            self._barrier(H_ext)
             self._push_input(H_ext)
         src = H_ext
         for k in range(1, K + 1):
@@ -899,6 +942,11 @@ class FusedPushPropagation:
                 self._barrier(dst)
             src = dst
         return Z_ext[: t.n_local]
+
+
+def _lib_mod():
+    from . import _lib
+    return _lib
 
 
 def _push_arrays(n_rows, rows, codes, dev):
@@ -1156,6 +1204,7 @@ class HybridPushPropagation:
         t = self.topo
         multi = t.world > 1
         if multi:
+            self._barrier(H_ext)          # entry barrier, see FusedPushPropagation.propagate
             self._push_input(H_ext)
         src = H_ext
         for k in range(1, K + 1):
@@ -1308,7 +1357,7 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
 
 
 def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4,
-                      carve=None, hub_degree=64, idx16=False, check_small=None):
+                      carve=None, hub_degree=64, idx16=False, check_small=None, rows_below=None, rows_order="dest"):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
@@ -1323,9 +1372,11 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         raise ValueError("carved shard streams exist for the fused transport (--transport fused, N > 1)")
 
     def make_prop(topo_, dinv_, carve_):
-        if transport in ("auto", "fused") and world > 1:
+        # the fused class also runs a single shard (no pushes, no barriers): T_1 of the scaling study then goes through
+        # exactly the kernels of the N > 1 runs (edge stream for the rows of high degree + rows kernel for the rest)
+        if transport in ("auto", "fused") and (world > 1 or rows_below):
             try:
-                pr = FusedPushPropagation(topo_, dinv_, carve=carve_, idx16=idx16)
+                pr = FusedPushPropagation(topo_, dinv_, carve=carve_, idx16=idx16, rows_below=rows_below, rows_order=rows_order)
                 pr.alloc(4, 1)                                  # peer mappings must be obtainable on this box
                 return pr
             except Exception as e:  # noqa: BLE001
@@ -1473,6 +1524,9 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     ms_exchange = timed(transfers_only)
 
     def compute_only():
+        if isinstance(prop, FusedPushPropagation):
+            prop._step(Z, H, S, alpha, _l.EPI_Y, False, False)
+            return
         first = True
         for p in prop.plans:
             if p is not None:
@@ -1497,8 +1551,10 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     nnz = int(sum(int(s[0]) for s in allstats))
     launches = 0
     for p in prop.plans:
-        if p is not None:
+        if p is not None and p.plan is not None:
             launches += 2 if p.plan.n_fix > 0 else 1
+    if getattr(prop, "rows_part", None) is not None:
+        launches += 1
     launches += (world - 1) if prop.transport_name in ("pull", "push") else 0
     if isinstance(prop, _PUSH_CLASSES):
         launches += (world - 1) * getattr(prop, "G", 0)
