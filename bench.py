@@ -681,7 +681,8 @@ def run_ours(args):
             tiled = {"slice_width": args.tiled_slice, "slack": args.tiled_slack, "fine_cols": args.tiled_fine_cols,
                      "rest": "rows" if args.rows_below else "stream"}
         graph = P.PropagationGraph(ahat, chunk_edges=args.chunk_edges, order=args.order, idx16=args.idx16, carve=carve, tiled=tiled,
-                                   rows_below=(args.rows_below or None) if not args.tiled else None)
+                                   rows_below=(args.rows_below or None) if not args.tiled else None,
+                                   window=({"key": args.window_key, "wide_cta": args.window_wide} if args.order == "window" else None))
     nnz = ahat.nnz
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
@@ -854,7 +855,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS) + ["pubmed_exact", "pubmed_batch"])
-    ap.add_argument("--order", default="degree", choices=["auto", "natural", "degree", "carve"],
+    ap.add_argument("--order", default="degree", choices=["auto", "natural", "degree", "carve", "window"],
                     help="processing order of the edge stream; auto times degree order and two L2-blocked carves and keeps the fastest")
     ap.add_argument("--idx16", dest="idx16", action="store_true", default=True,
                     help="16-byte staging of a lane-transposed index stream (default; bit-identical results)")
@@ -865,6 +866,8 @@ def main():
     ap.add_argument("--carve-narrow-cta", action="store_true", help="--order carve: keep the 256-thread CTAs")
     ap.add_argument("--carve-interleave", action="store_true", help="--order carve: alternate carved and residual chunk units")
     ap.add_argument("--carve-levels", default=None, help="--order carve: stacked block levels, e.g. 512x64x8,125000x16x16")
+    ap.add_argument("--window-key", default="mid", choices=["first", "mid", "last"], help="--order window: column of a chunk whose rank orders the chunks")
+    ap.add_argument("--window-wide", action="store_true", help="--order window: 1024-thread CTAs (64 consecutive chunks per SM)")
     ap.add_argument("--chunk-edges", type=int, default=256)
     ap.add_argument("--use-vals", action="store_true", help="stored-value form in every step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -9,7 +9,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .plan import StreamPlan, build_carved_plan, build_stream_plan, degree_order, lane_group_for, lane_transpose
+from .plan import (StreamPlan, build_carved_plan, build_stream_plan, degree_order, lane_group_for, lane_transpose,
+                   rank_sorted_csr, window_order_chunks)
 from .tiled import TiledPlan, build_tiled_plan
 
 MODE = {"sym": _lib.MODE_SYM, "rw": _lib.MODE_RW}
@@ -80,9 +81,12 @@ class PropagationGraph:
     """Normalised adjacency + edge-stream plan, ready for ``appnp_propagate``."""
 
     def __init__(self, ahat: NormalizedCSR, chunk_edges=256, order="natural", keep_vals=True, idx16=False, carve=None,
-                 tiled=None, rows_below=None):
-        """order: "natural" | "degree" | a permutation tensor (row-major streams, plan.build_stream_plan) or
-        "carve" (hot column blocks first, plan.build_carved_plan; ``carve`` = its keyword arguments).
+                 tiled=None, rows_below=None, window=None):
+        """order: "natural" | "degree" | a permutation tensor (row-major streams, plan.build_stream_plan),
+        "carve" (hot column blocks first, plan.build_carved_plan; ``carve`` = its keyword arguments) or
+        "window" (degree order with every row's columns sorted by rank and the whole-segment chunks of the hub
+        rows processed in column-window order, plan.window_order_chunks; ``window`` = {"key": "first" | "mid" |
+        "last", "wide_cta": bool}).
         idx16: stage the index stream with 16-byte copies from a lane-transposed copy of the stream
         (feature widths 16 and 64; other widths keep the linear stream).
         tiled: keyword arguments of ``tiled.build_tiled_plan`` plus ``slice_width`` (floats of the feature
@@ -125,6 +129,13 @@ class PropagationGraph:
                          if self._hub_order.numel() else None)
         elif isinstance(order, str) and order == "carve":
             self.plan: StreamPlan = build_carved_plan(ahat.indptr, ahat.indices, vals, chunk_edges, **(carve or {}))
+        elif isinstance(order, str) and order == "window":
+            wkw = dict(window or {})
+            sidx, svals, crank = rank_sorted_csr(ahat.indptr, ahat.indices, vals)
+            base = build_stream_plan(ahat.indptr, sidx, svals, chunk_edges, degree_order(ahat.indptr))
+            self.plan = window_order_chunks(base, crank, key=wkw.get("key", "mid"))
+            self.plan.wide_cta = bool(wkw.get("wide_cta", False))
+            del sidx, svals, crank, base
         else:
             if carve is not None:
                 raise ValueError("carve parameters need order='carve'")

@@ -264,6 +264,69 @@ def _plan_from_runs(n, run_row, run_len, stream_cols, stream_vals, chunk_edges, 
                       n_segs_real=n_segs)
 
 
+def column_ranks(indptr, indices, n_cols=None):
+    """Rank of every column by how many stored entries reference it (0 = hottest; ties by column id).  For the
+    symmetric A_hat that is the degree rank of the row."""
+    dev = indices.device
+    n = int(indptr.numel()) - 1
+    m_cols = n if n_cols is None else int(n_cols)
+    if n_cols is None:
+        ip = indptr.to(torch.int64)
+        refs = ip[1:] - ip[:-1]
+    else:
+        refs = torch.bincount(indices.to(torch.int64), minlength=m_cols)
+    corder = torch.sort(refs, descending=True, stable=True).indices
+    crank = torch.empty(m_cols, dtype=torch.int64, device=dev)
+    crank[corder] = torch.arange(m_cols, device=dev, dtype=torch.int64)
+    return crank
+
+
+def rank_sorted_csr(indptr, indices, vals=None, n_cols=None):
+    """The same CSR with the entries of every row sorted by the rank of their column (hottest first) instead of
+    the column id.  Which (row, column, value) triples exist does not change; only the order in which a row's
+    gathers are issued and added does.  Returns (indices, vals, crank)."""
+    dev = indices.device
+    n = int(indptr.numel()) - 1
+    ip = indptr.to(torch.int64)
+    crank = column_ranks(indptr, indices, n_cols)
+    m_cols = int(crank.numel())
+    row_of = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), ip[1:] - ip[:-1])
+    perm = torch.sort(row_of * m_cols + crank[indices.to(torch.int64)], stable=True).indices
+    return indices[perm].contiguous(), (None if vals is None else vals[perm].contiguous()), crank
+
+
+def permute_chunks(plan: StreamPlan, perm):
+    """Chunks are independent work items (``chunk_seg[c]`` points at a chunk's segments wherever the chunk sits):
+    process them in the order ``perm`` (new position -> old chunk).  Only cols / vals / chunk_seg move."""
+    if plan.lane_group:
+        raise ValueError("permute the chunks before the lane transposition")
+    nc, W = plan.n_chunks, plan.chunk_edges
+    perm = perm.to(device=plan.cols.device, dtype=torch.int64)
+    if perm.numel() != nc:
+        raise ValueError("perm must list every chunk once")
+    cols = plan.cols.view(nc, W)[perm].contiguous().view(-1)
+    vals = None if plan.vals is None else plan.vals.view(nc, W)[perm].contiguous().view(-1)
+    return StreamPlan(plan.n, plan.nnz, W, nc, cols, vals, plan.seg_row, plan.chunk_seg[perm].contiguous(), plan.fix_ptr,
+                      plan.fix_row, plan.fix_deg, plan.n_slots, plan.order, plan.n_segs_real, plan.row_deg,
+                      plan.wide_cta, plan.lane_group, plan.carve)
+
+
+def window_order_chunks(plan: StreamPlan, crank, key="first"):
+    """Process the chunks that hold ONE whole segment (the interior chunks of the hub rows, each already a partial
+    sum with its own slot) sorted by the rank of their ``key`` column (first / mid / last of the chunk) -- with
+    rank-sorted rows (``rank_sorted_csr``) all SMs then sweep the column space hot end first and together, so the
+    rows one warp gathers are L1 / L2 hits for the others.  No new partial sums: only whole chunks move.  The
+    remaining chunks follow in their old order."""
+    nc, W = plan.n_chunks, plan.chunk_edges
+    C = plan.cols.view(nc, W)
+    single = (C[:, :-1] >= 0).all(dim=1) & (C[:, -1] < 0)
+    pos = {"first": 0, "mid": W // 2, "last": W - 1}[key]
+    kcol = (C[:, pos] & 0x7FFFFFFF).to(torch.int64)
+    big = int(crank.numel())
+    k = torch.where(single, crank.to(plan.cols.device)[kcol], big + torch.arange(nc, device=plan.cols.device, dtype=torch.int64))
+    return permute_chunks(plan, torch.sort(k, stable=True).indices)
+
+
 def interleave_chunks(plan: StreamPlan, n_lead_chunks, unit_chunks=64):
     """Permute the chunks of ``plan`` so that units of ``unit_chunks`` consecutive chunks of its leading part
     (the first ``n_lead_chunks`` chunks: the carved pieces, served from L1) alternate evenly with units of

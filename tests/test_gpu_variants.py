@@ -14,6 +14,8 @@ VARIANTS = {
     "carve": dict(order="carve", carve=dict(block_cols=128, n_blocks=16, min_piece=3)),
     "carve+idx16": dict(order="carve", idx16=True, carve=dict(block_cols=128, n_blocks=16, min_piece=3)),
     "carve-narrow+idx16": dict(order="carve", idx16=True, carve=dict(block_cols=64, n_blocks=8, min_piece=2, wide_cta=False)),
+    "window+idx16": dict(order="window", idx16=True),
+    "window-wide+idx16": dict(order="window", idx16=True, window=dict(key="first", wide_cta=True)),
 }
 
 

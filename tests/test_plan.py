@@ -238,3 +238,46 @@ def test_two_level_carve_blocks_stack_along_the_rank_axis():
     blk = np.where(r < 128, r // 32, 4 + (r - 128) // 500)
     assert (np.diff(blk) >= 0).all() and blk.max() == 6
     assert relerr(walk_stream(two, H, H, 0.1, 0, True), oracle.appnp(ah, H, 0.1, 1)) < 1e-7
+
+
+def test_window_order_is_a_chunk_permutation_of_rank_sorted_rows_with_the_same_result():
+    """order="window": rows in degree order, a row's columns hottest first, whole-segment chunks by column window.
+    Cora-ML has one hub (246 neighbours); a synthetic skewed graph supplies many whole-segment chunks."""
+    from ppnp_b200.plan import rank_sorted_csr, window_order_chunks, column_ranks
+    for name, W in (("cora_ml", 128), ("rmat", 128)):
+        if name == "rmat":
+            rip, ridx = oracle.rmat_graph(3000, 200000, 12, seed=3)
+            oip, oidx, oval, _ = oracle.c_a_hat(rip, ridx, None, "sym")
+            import scipy.sparse as sp
+            ah = sp.csr_matrix((oval, oidx, oip), shape=(len(oip) - 1,) * 2)
+            ip, idx, val = torch.from_numpy(oip.astype(np.int32)), torch.from_numpy(oidx.astype(np.int32)), torch.from_numpy(oval.astype(np.float32))
+        else:
+            ah, ip, idx, val = ahat_tensors(name)
+        n = ah.shape[0]
+        H = np.random.RandomState(8).randn(n, 3)
+        sidx, sval, crank = rank_sorted_csr(ip, idx, val)
+        assert torch.equal(crank, column_ranks(ip, idx))
+        # same triples per row, columns by ascending rank
+        ipl = ip.to(torch.int64)
+        for r in (0, 1, int(torch.argmax(ipl[1:] - ipl[:-1]))):
+            a, b = int(ipl[r]), int(ipl[r + 1])
+            assert sorted(idx[a:b].tolist()) == sorted(sidx[a:b].tolist())
+            assert (np.diff(crank[sidx[a:b].to(torch.int64)].numpy()) > 0).all()
+        base = build_stream_plan(ip, sidx, sval, W, degree_order(ip))
+        win = window_order_chunks(base, crank, key="mid")
+        cb, cw = base.cols.view(base.n_chunks, W), win.cols.view(win.n_chunks, W)
+        assert sorted(zip(base.chunk_seg.tolist(), [tuple(r) for r in cb.tolist()])) == sorted(zip(win.chunk_seg.tolist(), [tuple(r) for r in cw.tolist()]))
+        single = ((cw[:, :-1] >= 0).all(1) & (cw[:, -1] < 0)).numpy()
+        k = int(single.sum())
+        if name == "rmat":
+            assert k > 50 and not torch.equal(base.cols, win.cols)
+        assert single[:k].all()                                   # they lead the stream ...
+        mid = crank[(cw[:k, W // 2] & 0x7FFFFFFF).to(torch.int64)].numpy()
+        assert (np.diff(mid) >= 0).all()                          # ... sorted by the rank of their middle column
+        ref = oracle.appnp(ah, H, 0.1, 1)
+        for use_vals, epi in ((True, 0),):
+            assert relerr(walk_stream(win, H, H, 0.1, epi, use_vals), ref) < 1e-7
+        assert np.array_equal(walk_stream(win, H, H, 0.1, 0, True), walk_stream(base, H, H, 0.1, 0, True))
+        # lane transposition composes with it
+        wt = lane_transpose(win, 16)
+        assert relerr(walk_stream(wt, H, H, 0.1, 0, True), ref) < 1e-7
