@@ -588,6 +588,7 @@ def run_ours(args):
                                        carve=({"block_cols": args.carve_block_cols, "n_blocks": args.carve_blocks,
                                                "min_piece": args.carve_min_piece} if args.order == "carve" else None),
                                        rows_below=(args.rows_below or None), rows_order=args.rows_order,
+                                       window=(args.window_key if args.order == "window" else None),
                                        check_small=(None if args.no_parity else
                                                     (lambda mk, al: parity_small_partitioned(mk, al, dev, rank, world, F, KSTEPS, ALPHA))))
         if rank == 0:

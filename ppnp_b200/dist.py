@@ -692,8 +692,11 @@ class FusedPushPropagation:
     MAX_PEERS = 8
 
     def __init__(self, topo: ShardTopology, deg_global_dinv, chunk_edges=256, group=None, step_fn=None, carve=None,
-                 idx16=False, rows_below=None, rows_order="dest"):
-        """carve: keyword arguments of plan.build_carved_plan (block_cols, n_blocks, min_piece): stream the
+                 idx16=False, rows_below=None, rows_order="dest", window=None):
+        """window: "first" | "mid" | "last": the rows of the edge stream keep their columns sorted by rank (hottest first)
+        and the whole-segment chunks of the hub rows are processed in column-window order (plan.window_order_chunks):
+        plan-only, no new partial sums; raises the L2 hit rate of the gathers.
+        carve: keyword arguments of plan.build_carved_plan (block_cols, n_blocks, min_piece): stream the
         shard with its hot column blocks first (blocks sized for the L2: the cold gathers of the hub rows
         stay inside an L2-resident window) instead of in plain degree order.
         idx16: 16-byte staging of a lane-transposed copy of the stream (feature widths 16 and 64), as on one GPU.
@@ -705,7 +708,9 @@ class FusedPushPropagation:
         (measured: 64-byte peer writes move at ~490 GB/s, profiles/r01_scaling.md).  "degree": descending degree
         (equal trip counts inside a warp), as on one GPU."""
         import ctypes as C
-        from .plan import build_carved_plan, build_stream_plan
+        from .plan import build_carved_plan, build_stream_plan, rank_sorted_csr, window_order_chunks
+        if carve and window:
+            raise ValueError("carve and window are alternative stream orders")
         self.topo, self.group, self._step_fn = topo, group, step_fn
         dev = topo.indices.device
         self.on_gpu = dev.type == "cuda"
@@ -731,9 +736,15 @@ class FusedPushPropagation:
                 self._low_rows = order[n_hub:]                     # ordered for good below, once the push lists exist
                 self._csr = (ip.to(torch.int32).contiguous(), topo.indices.to(torch.int32).contiguous(), vals.contiguous())
                 order = order[:n_hub]
-                plan = build_stream_plan(ip, topo.indices, vals, chunk_edges, order, subset=True) if n_hub else None
+                subset = True
             else:
-                plan = build_stream_plan(ip, topo.indices, vals, chunk_edges, order)
+                n_hub, subset = int(order.numel()), False
+            if window and n_hub:
+                sidx, svals, crank = rank_sorted_csr(ip, topo.indices, vals, n_cols=n_local + topo.n_halo)
+                plan = window_order_chunks(build_stream_plan(ip, sidx, svals, chunk_edges, order, subset=subset), crank, key=window)
+                del sidx, svals, crank
+            else:
+                plan = build_stream_plan(ip, topo.indices, vals, chunk_edges, order, subset=subset) if n_hub else None
         self.sub = _SubGraph(plan, step_fn)
         self.plans = [self.sub]
         self.idx16, self._plans16 = bool(idx16) and step_fn is None, {}
@@ -795,7 +806,8 @@ class FusedPushPropagation:
             self.rows_part = rs
         self.handles, self._bases = {}, {}
         self._C = C
-        self.transport_name = ("fused-push" if self.on_gpu else "fused-p2p") + ("" if self.rows_part is None else f"+rows<{rows_below}/{rows_order}")
+        self.transport_name = (("fused-push" if self.on_gpu else "fused-p2p") + ("" if self.rows_part is None else f"+rows<{rows_below}/{rows_order}")
+                               + (f"+window/{window}" if window else ""))
         self.phases, self.rounds = "one kernel per step, push in the epilogue", []
 
     def alloc(self, F, count=3):
@@ -1357,7 +1369,7 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
 
 
 def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4,
-                      carve=None, hub_degree=64, idx16=False, check_small=None, rows_below=None, rows_order="dest"):
+                      carve=None, hub_degree=64, idx16=False, check_small=None, rows_below=None, rows_order="dest", window=None):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
@@ -1368,15 +1380,16 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
-    if carve and not (transport in ("auto", "fused") and world > 1):
-        raise ValueError("carved shard streams exist for the fused transport (--transport fused, N > 1)")
+    if (carve or window) and transport not in ("auto", "fused"):
+        raise ValueError("carved / window-ordered shard streams exist for the fused transport (--transport fused)")
 
     def make_prop(topo_, dinv_, carve_):
         # the fused class also runs a single shard (no pushes, no barriers): T_1 of the scaling study then goes through
         # exactly the kernels of the N > 1 runs (edge stream for the rows of high degree + rows kernel for the rest)
-        if transport in ("auto", "fused") and (world > 1 or rows_below):
+        if transport in ("auto", "fused") and (world > 1 or rows_below or carve_ or window):
             try:
-                pr = FusedPushPropagation(topo_, dinv_, carve=carve_, idx16=idx16, rows_below=rows_below, rows_order=rows_order)
+                pr = FusedPushPropagation(topo_, dinv_, carve=carve_, idx16=idx16, rows_below=rows_below, rows_order=rows_order,
+                                          window=window)
                 pr.alloc(4, 1)                                  # peer mappings must be obtainable on this box
                 return pr
             except Exception as e:  # noqa: BLE001

@@ -281,18 +281,36 @@ def column_ranks(indptr, indices, n_cols=None):
     return crank
 
 
-def rank_sorted_csr(indptr, indices, vals=None, n_cols=None):
+def rank_sorted_csr(indptr, indices, vals=None, n_cols=None, max_batch_edges=1 << 27):
     """The same CSR with the entries of every row sorted by the rank of their column (hottest first) instead of
     the column id.  Which (row, column, value) triples exist does not change; only the order in which a row's
-    gathers are issued and added does.  Returns (indices, vals, crank)."""
+    gathers are issued and added does.  Sorted in row blocks of at most ``max_batch_edges`` entries so that the
+    temporaries stay small next to a multi-GB shard.  Returns (indices, vals, crank)."""
     dev = indices.device
     n = int(indptr.numel()) - 1
     ip = indptr.to(torch.int64)
     crank = column_ranks(indptr, indices, n_cols)
     m_cols = int(crank.numel())
-    row_of = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), ip[1:] - ip[:-1])
-    perm = torch.sort(row_of * m_cols + crank[indices.to(torch.int64)], stable=True).indices
-    return indices[perm].contiguous(), (None if vals is None else vals[perm].contiguous()), crank
+    out_idx = torch.empty_like(indices)
+    out_val = None if vals is None else torch.empty_like(vals)
+    nnz = int(ip[-1].item())
+    r0 = 0
+    while r0 < n:
+        # rows [r0, r1): as many whole rows as fit the batch (at least one)
+        lim = int(ip[r0].item()) + int(max_batch_edges)
+        r1 = int(torch.searchsorted(ip, torch.tensor([lim], device=dev, dtype=torch.int64), right=True).item()) - 1
+        r1 = min(max(r1, r0 + 1), n)
+        e0, e1 = int(ip[r0].item()), int(ip[r1].item())
+        if e1 > e0:
+            row_of = torch.repeat_interleave(torch.arange(r1 - r0, device=dev, dtype=torch.int64), ip[r0 + 1: r1 + 1] - ip[r0: r1])
+            perm = torch.sort(row_of * m_cols + crank[indices[e0:e1].to(torch.int64)], stable=True).indices
+            out_idx[e0:e1] = indices[e0:e1][perm]
+            if vals is not None:
+                out_val[e0:e1] = vals[e0:e1][perm]
+            del row_of, perm
+        r0 = r1
+    assert nnz == int(indices.numel())
+    return out_idx, out_val, crank
 
 
 def permute_chunks(plan: StreamPlan, perm):
@@ -316,14 +334,17 @@ def window_order_chunks(plan: StreamPlan, crank, key="first"):
     sum with its own slot) sorted by the rank of their ``key`` column (first / mid / last of the chunk) -- with
     rank-sorted rows (``rank_sorted_csr``) all SMs then sweep the column space hot end first and together, so the
     rows one warp gathers are L1 / L2 hits for the others.  No new partial sums: only whole chunks move.  The
-    remaining chunks follow in their old order."""
+    remaining chunks follow in their old order (merging them into the sweep at their rows' rank was modelled,
+    tools/window_model.py history, and loses: it stretches the hub sweep)."""
     nc, W = plan.n_chunks, plan.chunk_edges
+    dev = plan.cols.device
     C = plan.cols.view(nc, W)
     single = (C[:, :-1] >= 0).all(dim=1) & (C[:, -1] < 0)
     pos = {"first": 0, "mid": W // 2, "last": W - 1}[key]
     kcol = (C[:, pos] & 0x7FFFFFFF).to(torch.int64)
+    crank = crank.to(dev)
     big = int(crank.numel())
-    k = torch.where(single, crank.to(plan.cols.device)[kcol], big + torch.arange(nc, device=plan.cols.device, dtype=torch.int64))
+    k = torch.where(single, crank[kcol], big + torch.arange(nc, device=dev, dtype=torch.int64))
     return permute_chunks(plan, torch.sort(k, stable=True).indices)
 
 

@@ -76,6 +76,9 @@ def worker(rank, world, port, phases, outdir):
             prop = pd.FusedPushPropagation(topo, dinv, chunk_edges=128, step_fn=walker_step,
                                            carve=dict(block_cols=100, n_blocks=6, min_piece=3))
             assert prop.sub.plan.carve["carved_edges"] > 0 and not prop.sub.plan.wide_cta
+        elif phases == "fused-window":     # rank-sorted rows, whole-segment chunks in column-window order
+            prop = pd.FusedPushPropagation(topo, dinv, chunk_edges=128, step_fn=walker_step, window="mid")
+            assert "window/mid" in prop.transport_name
         elif phases.startswith("hybrid"):  # hub rows summed where their columns live (partial rows + combine launch)
             prop = pd.HybridPushPropagation(topo, dinv, hub_degree=int(phases[6:]), chunk_edges=128, step_fn=walker_step,
                                             alpha=alpha)
@@ -122,7 +125,7 @@ def worker(rank, world, port, phases, outdir):
 
 
 @pytest.mark.parametrize("world,phases", [(2, "peer"), (2, "one"), (3, "peer"), (3, "two"), (2, "pipe3"), (3, "pipe4"), (3, "pipe1"), (2, "fused"), (3, "fused"),
-                                          (2, "fused-carve"), (3, "fused-carve"),
+                                          (2, "fused-carve"), (3, "fused-carve"), (2, "fused-window"), (3, "fused-window"),
                                           (2, "hybrid8"), (3, "hybrid40"), (2, "hybrid100000")])
 def test_partitioned_propagation_gloo(tmp_path, world, phases):
     port = 29600 + world * 10 + len(phases) + (os.getpid() % 50)

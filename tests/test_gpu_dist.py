@@ -32,6 +32,8 @@ def worker(rank, world, port, mode, outdir):
             prop = pd.FusedPushPropagation(topo, dinv, idx16=True)
         elif transport == "fusedcarve":        # L2-sized hot column blocks of the shard first 
             prop = pd.FusedPushPropagation(topo, dinv, carve=dict(block_cols=16384, n_blocks=8, min_piece=8))
+        elif transport == "fusedwindow":       # rows kernel below `phases` entries, window-ordered hub stream
+            prop = pd.FusedPushPropagation(topo, dinv, rows_below=int(phases) or None, window="mid")
         elif transport == "fusedrows":         # low-degree rows through the rows kernel, ordered by destination slot / by degree
             prop = pd.FusedPushPropagation(topo, dinv, rows_below=int(phases.rstrip("d")), rows_order="degree" if phases.endswith("d") else "dest")
         elif transport == "hybrid":            # hub rows summed where their columns live 
@@ -46,7 +48,7 @@ def worker(rank, world, port, mode, outdir):
         old_of_new = np.argsort(new_of_old)
         mine = old_of_new[lo:hi]
         Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
-        H, Z, S = prop.alloc(F, 3) if transport in ("pipe", "fused", "fused16", "fusedcarve", "fusedrows", "hybrid") else prop.transport.alloc(F, 3)
+        H, Z, S = prop.alloc(F, 3) if transport in ("pipe", "fused", "fused16", "fusedcarve", "fusedrows", "fusedwindow", "hybrid") else prop.transport.alloc(F, 3)
         H.zero_()
         H[: topo.n_local] = torch.from_numpy(Hg[mine]).to(dev)
         out = prop.propagate(H, Z, S, K, alpha).cpu().numpy()
@@ -64,7 +66,8 @@ def worker(rank, world, port, mode, outdir):
 
 
 @pytest.mark.parametrize("mode", ["x/fused", "4/pipe", "1/pipe", "two/push", "one/push", "peer/pull", "peer/p2p", "one/p2p",
-                                  "x/fused16", "x/fusedcarve", "64/hybrid", "512/hybrid", "32/fusedrows", "32d/fusedrows", "1000000/fusedrows"])
+                                  "x/fused16", "x/fusedcarve", "64/hybrid", "512/hybrid", "32/fusedrows", "32d/fusedrows", "1000000/fusedrows",
+                                  "0/fusedwindow", "32/fusedwindow"])
 def test_partitioned_matches_oracle_on_two_gpus(tmp_path, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
