@@ -311,8 +311,14 @@ int ppnp_f32_to_bf16(const float* src, void* dst_bf16, int64_t count, void* stre
  *   ppnp_dense_row_nnz / ppnp_dense_to_csr: compact the masked matrix (entries > 0) to CSR.
  *   ppnp_batch_support: batch-main.py:140-141  sel = (ppr[idx_batch] > 0).any(0) on the compact
  *                      form: mark[j] = 1 for every column in the support of the batch rows.
+ *   ppnp_batch_support_colmap: batch-main.py:140-142 in ONE launch: sel[j] (one byte per column, 0/1: the
+ *                      bool mask of line 141) and colmap[j] = position of column j inside sel, -1 outside it
+ *                      (what line 142's ppr_sub[:, sel] amounts to on the compact form); *m_out = sel.sum()
+ *                      (nullable).  One CTA, one byte of shared memory per column: n_cols <= 204800, else
+ *                      PPNP_ENOTSUP (use ppnp_batch_support + a prefix sum).
  *   ppnp_batch_propagate: batch-main.py:142-146  logits = ppr[idx_batch][:, sel] @ Hsub where
- *                      Hsub = encoder(X[sel]); colmap[j] = position of column j in sel.
+ *                      Hsub = encoder(X[sel]); colmap[j] = position of column j in sel, or -1 for a
+ *                      column outside the mask (skipped, like the reference's column selection).
  *                      transpose != 0: the autograd adjoint dHsub = ppr_sub^T @ dlogits
  *                      (dHsub must be zeroed by the caller; accumulated with atomics).
  * ---------------------------------------------------------------------------------------- */
@@ -326,6 +332,9 @@ int ppnp_dense_to_csr(const float* ppr, int64_t n_rows, int64_t n_cols, int64_t 
                       const int64_t* indptr, int32_t* indices, float* val, void* stream);
 int ppnp_batch_support(const int64_t* indptr, const int32_t* indices, const int64_t* idx_batch,
                        int64_t B, uint8_t* mark, void* stream);
+int ppnp_batch_support_colmap(const int64_t* indptr, const int32_t* indices, const int64_t* idx_batch,
+                              int64_t B, int64_t n_cols, uint8_t* sel, int32_t* colmap, int32_t* m_out,
+                              void* stream);
 int ppnp_batch_propagate(const int64_t* indptr, const int32_t* indices, const float* val,
                          const int64_t* idx_batch, int64_t B, const int32_t* colmap,
                          const float* Hsub, int64_t ld_h, int32_t C, float* out, int64_t ld_out,

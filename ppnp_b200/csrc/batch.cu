@@ -23,6 +23,61 @@ batch_support_kernel(const int64_t* __restrict__ indptr, const int32_t* __restri
     for (int64_t t = b + lane; t < e; t += 32) mark[__ldg(indices + t)] = 1;
 }
 
+// The three lines batch-main.py:140-142 in ONE launch (a batch is small: B x k kept entries, n columns): one CTA
+// zeroes a byte flag per column in shared memory, marks the columns the batch rows keep, scans the flags and
+// writes sel[n] (the bool mask the caller indexes X with) and colmap[n] (position of a column inside the mask,
+// -1 outside it).  Replaces memset + mark + bool conversion + cumsum + subtract (5-7 launches per batch).
+constexpr int BSC_THREADS = 1024;
+
+__global__ void __launch_bounds__(BSC_THREADS)
+batch_support_colmap_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                            const int64_t* __restrict__ idx_batch, int64_t B, int n_cols,
+                            uint8_t* __restrict__ sel, int32_t* __restrict__ colmap, int32_t* __restrict__ m_out) {
+    extern __shared__ __align__(16) uint8_t flag[];     // n_cols rounded up to 16 bytes
+    __shared__ int warp_tot[BSC_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_words = (n_cols + 15) / 16 * 4;
+    for (int i = tid; i < n_words; i += BSC_THREADS) reinterpret_cast<uint32_t*>(flag)[i] = 0u;
+    __syncthreads();
+    for (int64_t w = warp; w < B; w += BSC_THREADS / 32) {
+        const int64_t r = idx_batch[w];
+        const int64_t b = indptr[r], e = indptr[r + 1];
+        for (int64_t t = b + lane; t < e; t += 32) flag[__ldg(indices + t)] = 1;    // benign same-value races
+    }
+    __syncthreads();
+    // every thread owns a contiguous span of columns; exclusive scan of the span counts over the CTA
+    const int per = (n_cols + BSC_THREADS - 1) / BSC_THREADS;
+    const int lo = min(tid * per, n_cols), hi = min(lo + per, n_cols);
+    int cnt = 0;
+    for (int c = lo; c < hi; ++c) cnt += flag[c];
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int v = warp_tot[lane];
+        int iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= o) iv += u;
+        }
+        warp_tot[lane] = iv - v;      // exclusive
+        if (lane == 31 && m_out != nullptr) *m_out = iv;
+    }
+    __syncthreads();
+    int pos = warp_tot[warp] + inc - cnt;
+    for (int c = lo; c < hi; ++c) {
+        const uint8_t f = flag[c];
+        sel[c] = f;
+        colmap[c] = f ? pos++ : -1;
+    }
+}
+
 // one warp per batch row; G lanes share one kept entry (G = pow2 >= C chunk), 32/G entries in flight
 template <int G>
 __global__ void __launch_bounds__(256)
@@ -43,8 +98,8 @@ batch_propagate_kernel(const int64_t* __restrict__ indptr, const int32_t* __rest
         for (int64_t t = b + sub; t < e; t += EPW) {
             const int col = __ldg(indices + t);
             const float v = __ldg(val + t);
-            const int pos = __ldg(colmap + col);
-            if (c < C) acc = fmaf(v, __ldg(Hsub + (int64_t)pos * ld_h + c), acc);
+            const int pos = __ldg(colmap + col);     // -1: column outside the mask (ppr_sub[:, mask] drops it)
+            if (c < C && pos >= 0) acc = fmaf(v, __ldg(Hsub + (int64_t)pos * ld_h + c), acc);
         }
 #pragma unroll
         for (int o = G; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -73,7 +128,7 @@ batch_propagate_t_kernel(const int64_t* __restrict__ indptr, const int32_t* __re
             const int col = __ldg(indices + t);
             const float v = __ldg(val + t);
             const int pos = __ldg(colmap + col);
-            if (c < C) atomicAdd(dH + (int64_t)pos * ld_dh + c, v * g);
+            if (c < C && pos >= 0) atomicAdd(dH + (int64_t)pos * ld_dh + c, v * g);
         }
     }
 }
@@ -90,6 +145,29 @@ int ppnp_batch_support(const int64_t* indptr, const int32_t* indices, const int6
     PPNP_REQUIRE(B > 0, "B > 0");
     batch_support_kernel<<<(unsigned)((B + 7) / 8), 256, 0, as_stream(stream)>>>(indptr, indices, idx_batch, B, mark);
     PPNP_CHECK_LAUNCH("batch_support_kernel");
+    return PPNP_OK;
+}
+
+int ppnp_batch_support_colmap(const int64_t* indptr, const int32_t* indices, const int64_t* idx_batch, int64_t B,
+                              int64_t n_cols, uint8_t* sel, int32_t* colmap, int32_t* m_out, void* stream) {
+    using namespace ppnp;
+    PPNP_REQUIRE(indptr && indices && idx_batch && sel && colmap, "null pointer");
+    PPNP_REQUIRE(B > 0 && n_cols > 0, "B > 0 and n_cols > 0");
+    const size_t smem = (size_t)((n_cols + 15) / 16) * 16;
+    if (smem > 200 * 1024) {
+        set_error("ppnp_batch_support_colmap keeps one byte per column in shared memory: n_cols <= %d", 200 * 1024);
+        return PPNP_ENOTSUP;
+    }
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(batch_support_colmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute batch_support_colmap_kernel");
+        if (rc) return rc;
+        configured = smem;
+    }
+    batch_support_colmap_kernel<<<1, BSC_THREADS, smem, as_stream(stream)>>>(indptr, indices, idx_batch, B, (int)n_cols, sel,
+                                                                            colmap, m_out);
+    PPNP_CHECK_LAUNCH("batch_support_colmap_kernel");
     return PPNP_OK;
 }
 

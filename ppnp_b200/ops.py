@@ -631,11 +631,27 @@ def dense_to_sparse_ppr(ppr):
     return SparsePPR(n_rows, n_cols, indptr, indices[:nnz], val[:nnz])
 
 
+_COLMAP_MAX_COLS = 200 * 1024       # ppnp_batch_support_colmap: one byte of shared memory per column
+
+
 def batch_support(sp_ppr: SparsePPR, idx_batch):
-    """batch-main.py:140-141 on the compact matrix: bool mask ``sel`` over the n columns."""
+    """batch-main.py:140-141 on the compact matrix: bool mask ``sel`` over the n columns.  One launch also yields
+    the column map line 142 needs (position of every column inside ``sel``, -1 outside); it rides on the returned
+    tensor (``sel._ppnp_colmap``) so that ``batch_propagate`` with this very mask starts no further kernel."""
     lib = _lib.load()
-    idx_batch = idx_batch.to(device=sp_ppr.indices.device, dtype=torch.int64).contiguous()
-    mark = torch.zeros(sp_ppr.n_cols, dtype=torch.uint8, device=sp_ppr.indices.device)
+    dev = sp_ppr.indices.device
+    idx_batch = idx_batch.to(device=dev, dtype=torch.int64).contiguous()
+    n = sp_ppr.n_cols
+    if idx_batch.numel() and n <= _COLMAP_MAX_COLS:
+        sel = torch.empty(n, dtype=torch.bool, device=dev)
+        colmap = torch.empty(n, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.ppnp_batch_support_colmap(_lib.ptr(sp_ppr.indptr), _lib.ptr(sp_ppr.indices), _lib.ptr(idx_batch),
+                                               idx_batch.numel(), n, _lib.ptr(sel), _lib.ptr(colmap), None, _lib.current_stream())
+        _lib.check(rc, "ppnp_batch_support_colmap")
+        sel._ppnp_colmap = (colmap, idx_batch)
+        return sel
+    mark = torch.zeros(n, dtype=torch.uint8, device=dev)
     if idx_batch.numel():
         with torch.cuda.device(mark.device):
             rc = lib.ppnp_batch_support(_lib.ptr(sp_ppr.indptr), _lib.ptr(sp_ppr.indices), _lib.ptr(idx_batch),
@@ -679,7 +695,13 @@ def batch_propagate(sp_ppr: SparsePPR, idx_batch, sel, Hsub):
     (differentiable w.r.t. Hsub)."""
     dev = sp_ppr.indices.device
     idx_batch = idx_batch.to(device=dev, dtype=torch.int64).contiguous()
-    colmap = (torch.cumsum(sel.to(torch.int32), 0, dtype=torch.int32) - 1).contiguous()
+    cached = getattr(sel, "_ppnp_colmap", None)
+    if cached is not None and (cached[1] is idx_batch or (cached[1].data_ptr() == idx_batch.data_ptr()
+                                                          and cached[1].numel() == idx_batch.numel())):
+        colmap = cached[0]                   # made by batch_support for this mask and this batch
+    else:                                    # any other mask: positions inside it, -1 outside (arbitrary masks are valid)
+        pos = torch.cumsum(sel.to(torch.int32), 0, dtype=torch.int32) - 1
+        colmap = torch.where(sel, pos, torch.full_like(pos, -1)).contiguous()
     return _BatchPropagateFunction.apply(Hsub, sp_ppr, idx_batch, colmap)
 
 

@@ -308,6 +308,26 @@ def test_batch_step_matches_reference_lines(name):
         out.backward(torch.from_numpy(Gn).to(dev()))
         dref = dense[idx_b][:, sel_ref].astype(np.float64).T @ Gn
         assert relerr(Hsub.grad.cpu().numpy(), dref) < 1e-5
+        # the one-launch form: the same index tensor for both calls -> the column map made with the mask is used
+        ib = torch.from_numpy(idx_b).to(dev())
+        sel1 = P.batch_support(spp, ib)
+        colmap, _ = sel1._ppnp_colmap
+        want = np.where(sel_ref, np.cumsum(sel_ref) - 1, -1)
+        assert np.array_equal(sel1.cpu().numpy(), sel_ref) and np.array_equal(colmap.cpu().numpy(), want)
+        H1 = torch.from_numpy(g["H"]).to(dev())[sel1].requires_grad_(True)
+        out1 = P.batch_propagate(spp, ib, sel1, H1)
+        assert torch.equal(out1, out)
+        out1.backward(torch.from_numpy(Gn).to(dev()))
+        assert relerr(H1.grad.cpu().numpy(), dref) < 1e-5
+        # arbitrary masks are valid, like the reference's ppr_sub[:, mask] (columns outside the mask are dropped)
+        rs = np.random.RandomState(seed + 1)
+        for mask in (sel_ref | (rs.rand(len(sel_ref)) < 0.3), sel_ref & (rs.rand(len(sel_ref)) < 0.6)):
+            if not mask.any():
+                continue
+            tm = torch.from_numpy(mask).to(dev())
+            outm = P.batch_propagate(spp, ib, tm, torch.from_numpy(g["H"]).to(dev())[tm])
+            refm = dense[idx_b][:, mask].astype(np.float64) @ g["H"].astype(np.float64)[mask]
+            assert relerr(outm.cpu().numpy(), refm) < 1e-5
 
 
 # ------------------------------------------------------------------ persistent K-step kernel
