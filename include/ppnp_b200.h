@@ -341,6 +341,32 @@ int ppnp_batch_propagate(const int64_t* indptr, const int32_t* indices, const fl
                          int32_t transpose, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (4b) Edge-stream plan, built on the GPU (csrc/plan_build.cu).  No counterpart in the reference: the stream is a
+ *      re-encoding of the CSR that helpers.py:58-63 (calc_A_hat) produces, in a caller-chosen processing order of
+ *      the rows.  Host mirror and specification: ppnp_b200/plan.py build_stream_plan / lane_transpose.
+ *   ppnp_plan_workspace_bytes: scratch for ppnp_plan_measure over n_listed rows.
+ *   ppnp_plan_measure: order[n_listed] (int64, nullable = natural order) lists the rows to stream.  Outputs, each
+ *                      [n_listed + 1]: row_start (stream position of a row; last = edges in the stream), seg_first,
+ *                      slot_first, fix_first (first segment / partial slot / cut-row index of a row; last = totals);
+ *                      totals[5] (device) = {edges, segments, partial slots, cut rows, listed rows without an edge}.
+ *                      The caller reads totals, allocates the plan arrays and calls
+ *   ppnp_plan_fill   : cols[n_chunks * chunk_edges] (bit 31 = last edge of a segment; lane_group > 0: stored
+ *                      lane-transposed, PPNP_PLAN_LANE_GROUP), out_vals (nullable with vals), seg_row[n_segs],
+ *                      chunk_seg[n_chunks], fix_ptr[n_fix + 1], fix_row[n_fix], fix_deg[n_fix] (row_deg[row] when
+ *                      row_deg is given, else the row's edge count).  Padding edges point at column 0.
+ * ---------------------------------------------------------------------------------------- */
+int64_t ppnp_plan_workspace_bytes(int64_t n_listed);
+int ppnp_plan_measure(const int64_t* indptr, const int64_t* order, int64_t n_listed, int32_t chunk_edges,
+                      int64_t* row_start, int32_t* seg_first, int32_t* slot_first, int32_t* fix_first,
+                      int64_t* totals, void* workspace, int64_t workspace_bytes, void* stream);
+int ppnp_plan_fill(const int64_t* indptr, const int32_t* indices, const float* vals, const int64_t* order,
+                   int64_t n_listed, int32_t chunk_edges, int32_t lane_group, const int64_t* row_start,
+                   const int32_t* seg_first, const int32_t* slot_first, const int32_t* fix_first,
+                   const float* row_deg, int64_t nnz, int64_t n_chunks, int64_t n_segs, int64_t n_fix,
+                   int32_t* cols, float* out_vals, int32_t* seg_row, int32_t* chunk_seg, int32_t* fix_ptr,
+                   int32_t* fix_row, float* fix_deg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (5) Partitioned propagation helper (BASELINE config 5; no counterpart in the single-process
  *     reference): dst[i, :] = src[idx[i], :] for i < n_rows.  src may be a peer GPU's buffer mapped
  *     over NVLink (halo pull) or the local Z (pack in front of an NCCL send).

@@ -80,6 +80,10 @@ SIGNATURES = {
     "ppnp_batch_support": (C.c_int, [_p, _p, _p, _i64, _p, _p]),
     "ppnp_batch_support_colmap": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "ppnp_batch_propagate": (C.c_int, [_p, _p, _p, _p, _i64, _p, _p, _i64, _i32, _p, _i64, _i32, _p]),
+    "ppnp_plan_workspace_bytes": (_i64, [_i64]),
+    "ppnp_plan_measure": (C.c_int, [_p, _p, _i64, _i32, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "ppnp_plan_fill": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64,
+                                 _p, _p, _p, _p, _p, _p, _p, _p]),
     "ppnp_gather_rows": (C.c_int, [_p, _i64, _p, _i64, _i32, _p, _i64, _p]),
     "ppnp_rmat_keys": (C.c_int, [_u64, _i32, _i64, _i64, _i64, _p, _p]),
     "ppnp_graph_standardize_workspace_bytes": (_i64, [_i64, _i64, _i32]),

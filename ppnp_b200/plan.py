@@ -14,6 +14,8 @@ produces; processing order and cuts never change which (row, column, value) trip
 from dataclasses import dataclass, field
 from typing import Optional
 
+import os
+
 import torch
 
 from . import _lib
@@ -89,6 +91,73 @@ class StreamPlan:
                           self.wide_cta, self.lane_group, self.carve)
 
 
+def build_stream_plan_cuda(indptr, indices, vals=None, chunk_edges=256, order=None, subset=False, row_deg=None, lane_group=0):
+    """``build_stream_plan`` (and, with ``lane_group`` > 0, ``lane_transpose`` on top of it) by the CUDA builder
+    csrc/plan_build.cu: four scans over the listed rows and one pass over the edges instead of ~15 eager tensor
+    passes over int64 temporaries of nnz entries.  Same arrays, bit for bit (tests/test_gpu_plan_build.py)."""
+    if chunk_edges % 128 != 0 or chunk_edges <= 0:
+        raise ValueError("chunk_edges must be a positive multiple of 128")
+    if not indices.is_cuda:
+        raise RuntimeError("build_stream_plan_cuda: CUDA tensors required")
+    lib = _lib.load()
+    dev = indices.device
+    n = int(indptr.numel()) - 1
+    ip = indptr.to(device=dev, dtype=torch.int64).contiguous()
+    idx32 = indices.to(torch.int32).contiguous()
+    v32 = None if vals is None else vals.to(torch.float32).contiguous()
+    if order is not None:
+        order = order.to(device=dev, dtype=torch.int64).contiguous()
+        if not subset and order.numel() != n:
+            raise ValueError("order must list every row once (pass subset=True for a partial stream)")
+    m = n if order is None else int(order.numel())
+    if m == 0:
+        raise ValueError("no rows to stream")
+    if row_deg is not None:
+        row_deg = row_deg.to(device=dev, dtype=torch.float32).contiguous()
+    W = int(chunk_edges)
+    row_start = torch.empty(m + 1, dtype=torch.int64, device=dev)
+    seg_first = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    slot_first = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    fix_first = torch.empty(m + 1, dtype=torch.int32, device=dev)
+    totals = torch.empty(5, dtype=torch.int64, device=dev)
+    ws_bytes = int(lib.ppnp_plan_workspace_bytes(m))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.ppnp_plan_measure(_lib.ptr(ip), _lib.ptr(order), m, W, _lib.ptr(row_start), _lib.ptr(seg_first), _lib.ptr(slot_first),
+                                   _lib.ptr(fix_first), _lib.ptr(totals), _lib.ptr(ws), ws_bytes, _lib.current_stream())
+        _lib.check(rc, "ppnp_plan_measure")
+        nnz, n_segs, n_slots, n_fix, n_empty, nnz_csr = totals.tolist() + [int(ip[-1].item())]
+        if nnz_csr != int(indices.numel()):
+            raise ValueError("indptr[-1] != len(indices)")
+        if n_empty:
+            raise ValueError("every streamed row needs at least one edge (A_hat rows hold their self loop)")
+        if nnz // W + m >= (1 << 31):
+            raise ValueError("stream too long for 32-bit segment indices")
+        n_chunks = ((((nnz + W - 1) // W) + 31) // 32) * 32
+        cols = torch.empty(n_chunks * W, dtype=torch.int32, device=dev)
+        svals = None if v32 is None else torch.empty(n_chunks * W, dtype=torch.float32, device=dev)
+        # 64 spare entries: the kernel prefetches seg_row[s + lane] without a bounds check
+        seg_row = torch.empty(n_segs + 64, dtype=torch.int32, device=dev)
+        seg_row[n_segs:] = 0
+        chunk_seg = torch.empty(n_chunks, dtype=torch.int32, device=dev)
+        fix_ptr = torch.empty(n_fix + 1, dtype=torch.int32, device=dev)
+        fix_row = torch.empty(n_fix, dtype=torch.int32, device=dev)
+        fix_deg = torch.empty(n_fix, dtype=torch.float32, device=dev)
+        rc = lib.ppnp_plan_fill(_lib.ptr(ip), _lib.ptr(idx32), _lib.ptr(v32), _lib.ptr(order), m, W, int(lane_group), _lib.ptr(row_start),
+                                _lib.ptr(seg_first), _lib.ptr(slot_first), _lib.ptr(fix_first), _lib.ptr(row_deg), nnz, n_chunks,
+                                n_segs, n_fix, _lib.ptr(cols), _lib.ptr(svals), _lib.ptr(seg_row), _lib.ptr(chunk_seg),
+                                _lib.ptr(fix_ptr), _lib.ptr(fix_row) if n_fix else None, _lib.ptr(fix_deg) if n_fix else None,
+                                _lib.current_stream())
+        _lib.check(rc, "ppnp_plan_fill")
+    return StreamPlan(n=n, nnz=nnz, chunk_edges=W, n_chunks=n_chunks, cols=cols, vals=svals, seg_row=seg_row, chunk_seg=chunk_seg,
+                      fix_ptr=fix_ptr, fix_row=fix_row, fix_deg=fix_deg, n_slots=n_slots, order=order, n_segs_real=n_segs,
+                      row_deg=row_deg, lane_group=int(lane_group))
+
+
+def _cuda_builder_enabled():
+    return os.environ.get("PPNP_PLAN_BUILDER", "cuda").lower() != "torch"
+
+
 def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None, subset=False, row_deg=None):
     """Cut the CSR (indptr[n+1], indices[nnz], optional vals[nnz]) into the edge stream.
 
@@ -96,7 +165,18 @@ def build_stream_plan(indptr, indices, vals=None, chunk_edges=256, order=None, s
     relabelled, so inputs and outputs of the propagation keep the caller's row order.  With
     ``subset=True`` ``order`` may list only some rows: the stream then produces exactly those rows
     (used to split a shard into interior and boundary rows, ppnp_b200/dist.py).
+
+    CUDA tensors go through the CUDA builder (``build_stream_plan_cuda``; ``PPNP_PLAN_BUILDER=torch`` keeps the
+    tensor-op form below, which is also the host mirror the CPU tests walk and the specification the CUDA
+    builder is checked against bit for bit).
     """
+    if indices.is_cuda and _cuda_builder_enabled():
+        return build_stream_plan_cuda(indptr, indices, vals, chunk_edges, order, subset, row_deg)
+    return build_stream_plan_torch(indptr, indices, vals, chunk_edges, order, subset, row_deg)
+
+
+def build_stream_plan_torch(indptr, indices, vals=None, chunk_edges=256, order=None, subset=False, row_deg=None):
+    """``build_stream_plan`` with torch tensor ops on whatever device the CSR lives on (host mirror / specification)."""
     if chunk_edges % 128 != 0 or chunk_edges <= 0:
         raise ValueError("chunk_edges must be a positive multiple of 128")
     dev = indices.device
