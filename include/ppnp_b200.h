@@ -34,6 +34,10 @@ extern "C" {
 /* 'sym' with the input ALREADY scaled, H_in = D^-1/2 H (the fused encoder tail, ppnp_linear_rowscale, writes it
  * that way): every step is value-free, the stored values of A_hat are never read and need not exist. */
 #define PPNP_MODE_SYM_Y0 2
+/* OR-ed into the `mode` argument of ppnp_appnp_propagate: always run the K steps as per-step launches, never as the
+ * one-launch cooperative kernel that small graphs get by default (tests of the per-step epilogues on small graphs,
+ * callers that must not use cooperative launches). */
+#define PPNP_MODE_PER_STEP 0x100
 
 /* epilogue of one propagation step, out[r] = a(deg_r) * acc_r + b(deg_r) * T[r] */
 #define PPNP_EPI_PLAIN 0   /* a = 1-alpha,            b = alpha            stored values, Z-space         */

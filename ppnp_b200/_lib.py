@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("PPNP_B200_LIB") or os.path.join(_HERE, "libppnp_b200.
 
 # epilogues / modes (keep in sync with include/ppnp_b200.h)
 MODE_SYM, MODE_RW, MODE_SYM_Y0 = 0, 1, 2
+MODE_PER_STEP = 0x100      # PPNP_MODE_PER_STEP: never the one-launch cooperative kernel
 EPI_PLAIN, EPI_Z2Y, EPI_Y, EPI_Y2Z, EPI_RW, EPI_Y02Z = 0, 1, 2, 3, 4, 5
 EPI_ACC = 16
 EPI_INPLACE = 32

@@ -178,6 +178,7 @@ extern "C" int ppnp_appnp_propagate_parts(const ppnp_tiled_plan_t* tiled, const 
     PPNP_REQUIRE(tiled || stream_plan || rows, "at least one part is required");
     PPNP_REQUIRE(H && Z && scratch && H != Z && H != scratch && Z != scratch, "H, Z, scratch must be distinct buffers");
     PPNP_REQUIRE(K >= 1, "K >= 1");
+    mode &= ~PPNP_MODE_PER_STEP;      // this entry point always launches per step
     PPNP_REQUIRE(mode == PPNP_MODE_SYM || mode == PPNP_MODE_RW || mode == PPNP_MODE_SYM_Y0, "bad mode");
     const float* src = H;
     for (int k = 1; k <= K; ++k) {

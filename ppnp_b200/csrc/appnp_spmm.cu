@@ -823,13 +823,15 @@ int ppnp_appnp_propagate(const ppnp_plan_t* plan, const float* H, float* Z, floa
     PPNP_REQUIRE(F > 0 && ld >= F && ld < ((int64_t)1 << 30), "need 0 < F <= ld < 2^30");
     PPNP_REQUIRE(K >= 1, "K >= 1");
     PPNP_REQUIRE(plan->n_slots == 0 || partial != nullptr, "partial buffer required");
+    const bool per_step = (mode & PPNP_MODE_PER_STEP) != 0;
+    mode &= ~PPNP_MODE_PER_STEP;
     PPNP_REQUIRE(mode == PPNP_MODE_SYM || mode == PPNP_MODE_RW || mode == PPNP_MODE_SYM_Y0, "bad mode");
     PPNP_REQUIRE(mode != PPNP_MODE_SYM_Y0 || !use_vals, "PPNP_MODE_SYM_Y0 is value-free");
     PPNP_REQUIRE(!(use_vals || (mode == PPNP_MODE_SYM)) || plan->vals != nullptr,
                  "plan->vals required (stored-value steps / first 'sym' step)");
     cudaStream_t stream = as_stream(stream_);
     // small graphs: all K steps in one cooperative launch (grid barriers instead of 2K launches)
-    if (K >= 2 && mode != PPNP_MODE_SYM_Y0 && plan->vals != nullptr && plan->row_deg == nullptr && plan->n_chunks <= PPNP_PERSISTENT_MAX_CHUNKS &&
+    if (!per_step && K >= 2 && mode != PPNP_MODE_SYM_Y0 && plan->vals != nullptr && plan->row_deg == nullptr && plan->n_chunks <= PPNP_PERSISTENT_MAX_CHUNKS &&
         PPNP_PLAN_LANE_GROUP(plan->flags) == 0 && persistent_enabled()) {
         return dispatch_persistent(plan, H, Z, scratch, partial, ld, F, K, alpha, stream);
     }

@@ -264,13 +264,16 @@ def spmm_step(graph: PropagationGraph, Zin, T, alpha, epi=_lib.EPI_PLAIN, use_va
     return out
 
 
-def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False, out=None, scratch=None, scaled_input=False):
+def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False, out=None, scratch=None, scaled_input=False,
+                    per_step=False):
     """K steps of Z <- (1-alpha) A_hat Z + alpha H from Z_0 = H (north_star; forward and backward).
 
     ``use_vals=False`` runs the value-free Y-space iteration (stored values only in step 1),
     ``use_vals=True`` multiplies by the stored A_hat values in every step.
     ``scaled_input=True``: ``H`` holds D^-1/2 H already (``linear_rowscale`` writes it that way): every step is
     value-free, the stored values are never read (PPNP_MODE_SYM_Y0); the result is the same Z.
+    ``per_step=True``: K launches (+ fix-ups) even on a graph small enough for the one-launch cooperative kernel
+    (PPNP_MODE_PER_STEP).
     """
     lib = _lib.load()
     _require_cuda(H)
@@ -286,7 +289,7 @@ def appnp_propagate(graph: PropagationGraph, H, K=10, alpha=0.1, use_vals=False,
         raise ValueError("scaled_input is the value-free 'sym' iteration on a unit-weight graph")
     if not graph.unit_weights:
         use_vals = True     # edge counts are not degrees here: the value-free form would be silently wrong
-    mode_code = _lib.MODE_SYM_Y0 if scaled_input else MODE[graph.mode]
+    mode_code = (_lib.MODE_SYM_Y0 if scaled_input else MODE[graph.mode]) | (_lib.MODE_PER_STEP if per_step else 0)
     Z = out if out is not None else torch.empty_like(H)
     scratch = scratch if scratch is not None else torch.empty_like(H)
     tiled, stream_plan, rows, W, partial = graph.parts_for(F)

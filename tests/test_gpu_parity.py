@@ -76,15 +76,24 @@ def test_rmat_device_generator_matches_host():
 @pytest.mark.parametrize("name", NAMES)
 @pytest.mark.parametrize("use_vals", [False, True])
 @pytest.mark.parametrize("order", ["natural", "degree"])
-def test_appnp_matches_restatement(name, use_vals, order):
+@pytest.mark.parametrize("per_step", [False, True], ids=["one-launch", "per-step"])
+def test_appnp_matches_restatement(name, use_vals, order, per_step):
+    """per_step=False: graphs this small run all K steps in the cooperative kernel (stored values in every step, so
+    ``use_vals`` changes nothing there); per_step=True: the K per-step launches with the Z2Y / Y / Y2Z epilogues of the
+    value-free form (or the plain epilogue with stored values) on the same golden graphs."""
     import ppnp_b200 as P
     ahat, adj = gpu_ahat(name)
     g = load_golden(name)
     graph = P.PropagationGraph(ahat, chunk_edges=128, order=order)
     H = torch.from_numpy(g["H"]).to(dev())
-    Z = P.appnp_propagate(graph, H, K=10, alpha=0.1, use_vals=use_vals).cpu().numpy()
+    Zt = P.appnp_propagate(graph, H, K=10, alpha=0.1, use_vals=use_vals, per_step=per_step)
+    Z = Zt.cpu().numpy()
     assert relerr(Z, g["appnp_K10"]) < 1e-5                      # north_star fp32 tolerance
     assert (Z.argmax(1) == g["appnp_K10"].argmax(1)).all()       # identical argmax on frozen H
+    if per_step:
+        one = P.appnp_propagate(graph, H, K=10, alpha=0.1, use_vals=use_vals)
+        assert not torch.equal(one, Zt) or use_vals              # really another path (other order of additions) ...
+        assert float((one - Zt).norm() / one.norm()) < 1e-6      # ... with the same answer
 
 
 @pytest.mark.parametrize("F", [1, 3, 7, 16, 20, 64, 100, 256])
