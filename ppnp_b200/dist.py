@@ -1500,7 +1500,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     dist.barrier()
     s_in.wait_stream(cur)
     s_out.wait_stream(cur)
-    e2e_steps = 3
+    e2e_steps = max(3, min(int(steps), 8))
     e0.record()
     for _ in range(e2e_steps):
         one_pass_e2e()
