@@ -25,6 +25,10 @@ namespace {
 constexpr int PPR_THREADS = 128;
 constexpr int PPR_CPT = 4;                        // columns per thread
 constexpr int PPR_TILE = PPR_THREADS * PPR_CPT;   // 512 columns: n * 2 KB per slab
+#ifndef PPNP_PPR_ROWS
+#define PPNP_PPR_ROWS 8                           // rows per CTA of a step: one CTA per (row, tile) is 769 k CTAs of ~13 KB
+#endif                                            // of traffic each at PubMed shape -- the block scheduler, not HBM, sets the pace
+constexpr int PPR_ROWS = PPNP_PPR_ROWS;
 
 // Pi_1 = (1-alpha) A_hat + alpha I, written densely (one CTA per row).
 __global__ void __launch_bounds__(256)
@@ -61,8 +65,9 @@ __global__ void __launch_bounds__(PPR_THREADS)
 ppr_step_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const float* __restrict__ val, int64_t n, float alpha,
                 const float* __restrict__ Pin, float* Pout, float omega, int prev_identity) {
-    const int64_t i = blockIdx.x;
     const int64_t c0 = (int64_t)blockIdx.y * PPR_TILE + threadIdx.x;
+    const int64_t i_end = ((int64_t)blockIdx.x + 1) * PPR_ROWS < n ? ((int64_t)blockIdx.x + 1) * PPR_ROWS : n;
+    for (int64_t i = (int64_t)blockIdx.x * PPR_ROWS; i < i_end; ++i) {
     float acc[PPR_CPT];
 #pragma unroll
     for (int k = 0; k < PPR_CPT; ++k) acc[k] = 0.f;
@@ -109,6 +114,7 @@ ppr_step_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
             }
         }
     }
+    }
 }
 
 }  // namespace
@@ -131,7 +137,7 @@ extern "C" int ppnp_ppr_dense(const int32_t* indptr, const int32_t* indices, con
     float* dst = ((K - 1) % 2 == 0) ? Pi : scratch;
     ppr_init_kernel<<<(unsigned)n, 256, 0, stream>>>(indptr, indices, val, n, alpha, dst);
     PPNP_CHECK_LAUNCH("ppr_init_kernel");
-    const dim3 grid((unsigned)n, (unsigned)((n + PPR_TILE - 1) / PPR_TILE));
+    const dim3 grid((unsigned)((n + PPR_ROWS - 1) / PPR_ROWS), (unsigned)((n + PPR_TILE - 1) / PPR_TILE));
     for (int k = 2; k <= K; ++k) {
         const float* src = dst;
         dst = ((K - k) % 2 == 0) ? Pi : scratch;
@@ -155,7 +161,7 @@ extern "C" int ppnp_ppr_dense_cheb(const int32_t* indptr, const int32_t* indices
     float* b = (K % 2 == 1) ? scratch : Pi;
     ppr_init_kernel<<<(unsigned)n, 256, 0, stream>>>(indptr, indices, val, n, alpha, a);      // x_1 = G I + alpha I
     PPNP_CHECK_LAUNCH("ppr_init_kernel");
-    const dim3 grid((unsigned)n, (unsigned)((n + PPR_TILE - 1) / PPR_TILE));
+    const dim3 grid((unsigned)((n + PPR_ROWS - 1) / PPR_ROWS), (unsigned)((n + PPR_TILE - 1) / PPR_TILE));
     const double rho2 = (1.0 - (double)alpha) * (1.0 - (double)alpha);
     double w = 1.0;
     for (int k = 2; k <= K; ++k) {

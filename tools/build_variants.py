@@ -16,6 +16,11 @@ VARIANTS = {
     # slabs with <= 2 segment ends per lane group keep the rolling gather ring (profiles/r01_variants.md, point 3)
     "fewends": ["PPNP_SPMM_FEWENDS=1"],
     "fewends_segpred": ["PPNP_SPMM_FEWENDS=1", "PPNP_SPMM_SEGPRED=1"],
+    # rows per CTA of the dense-Pi build step (csrc/ppr_dense.cu)
+    "pprrows1": ["PPNP_PPR_ROWS=1"],
+    "pprrows4": ["PPNP_PPR_ROWS=4"],
+    "pprrows16": ["PPNP_PPR_ROWS=16"],
+    "pprrows32": ["PPNP_PPR_ROWS=32"],
 }
 
 if __name__ == "__main__":
