@@ -325,12 +325,12 @@ def parity_small_partitioned(make_prop, alloc_of, dev, rank, world, F, K, alpha)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ppnp_oracle as oracle       # checker only
     n, raw, scale = 204_800, 3_000_000, 18
-    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world, batch=1 << 20)
+    indptr, cols, bounds, relabel = rmat_shard(n, raw, scale, 0, dev, rank, world, batch=1 << 20, return_relabel=True)
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     pr = make_prop(topo, dinv, None)
     H, Z, S = alloc_of(pr, 3)
-    new_of_old = stripe_relabel(torch.arange(n), n, world, auto_stripes(n, world)).numpy()
+    new_of_old = relabel.cpu().numpy()         # generator ids -> the partitioner's ids (stripes, then degree order inside a block)
     mine = np.argsort(new_of_old)[bounds[rank]: bounds[rank + 1]]
     Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
     for b in (H, Z, S):
@@ -589,6 +589,7 @@ def run_ours(args):
                                                "min_piece": args.carve_min_piece} if args.order == "carve" else None),
                                        rows_below=(args.rows_below or None), rows_order=args.rows_order,
                                        window=(args.window_key if args.order == "window" else None),
+                                       degree_sort=not args.no_degree_sort,
                                        check_small=(None if args.no_parity else
                                                     (lambda mk, al: parity_small_partitioned(mk, al, dev, rank, world, F, KSTEPS, ALPHA))))
         if rank == 0:
@@ -892,6 +893,8 @@ def main():
     ap.add_argument("--stripes", type=int, default=0, help="multi-GPU: block-cyclic stripes per rank (0 = auto, ~4096-id stripes; 1 = plain contiguous blocks)")
     ap.add_argument("--dist-idx16", action="store_true", help="multi-GPU fused transport: 16-byte index staging (validated on one GPU only)")
     ap.add_argument("--hub-degree", type=int, default=64, help="multi-GPU --transport hybrid: rows of at least this degree are summed where their columns live")
+    ap.add_argument("--no-degree-sort", action="store_true", help="partitioned path: keep the generator's order of the rows inside a block "
+                    "(default: rows of a block are stored by descending degree, so that hot 64-byte rows share their 128-byte lines)")
     ap.add_argument("--transport", default="auto", choices=["auto", "fused", "hybrid", "pipe", "pull", "push", "p2p"], help="multi-GPU: halo transport")
     args = ap.parse_args()
     if args.impl == "reference":

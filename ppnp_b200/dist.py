@@ -1292,23 +1292,50 @@ def auto_stripes(n, world, target_block=4096):
     return 1
 
 
-def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group=None, stripes=0):
+def degree_sort_relabel(w, bounds):
+    """Second relabelling, inside every rank's block: ids by descending weight ``w`` (ties by id).  Rows of the feature
+    matrices are STORED in id order, so this puts a block's hot rows next to each other in memory: at F = 16 a row is
+    64 bytes, half a 128-byte line -- packed by degree the lines of the hot set are all useful, in the generator's
+    order every hot row drags a cold line-mate through the L2 (measured on one GPU, 16 M nodes, F = 16: 5.53 -> 4.74
+    ms per step; random ids: 7.1; no effect at F = 64 -- profiles/r02_relabel_probe.txt).  Block membership, hence
+    the non-zero balance of the cut, does not change.  Returns new_of_old (int64 [n])."""
+    n = int(w.numel())
+    new_of_old = torch.empty(n, dtype=torch.int64, device=w.device)
+    for p in range(len(bounds) - 1):
+        lo, hi = bounds[p], bounds[p + 1]
+        if hi > lo:
+            order = torch.sort(w[lo:hi], descending=True, stable=True).indices
+            new_of_old[lo + order] = torch.arange(lo, hi, device=w.device, dtype=torch.int64)
+    return new_of_old
+
+
+def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group=None, stripes=0, degree_sort=True,
+               return_relabel=False):
     """Rows of A + I of the R-MAT graph owned by ``rank`` (global column ids) and the partition.
     Pass 1 estimates the per-row weight from the raw draws to place the boundaries by non-zeros;
     pass 2 keeps the (de-duplicated) edges whose row falls inside this rank's block.  Vertex ids
-    are the striped relabelling of the generator's ids (``stripe_relabel``)."""
+    are the striped relabelling of the generator's ids (``stripe_relabel``) followed, with
+    ``degree_sort``, by ``degree_sort_relabel`` inside every block (both are the partitioner's choice of
+    row order; ``return_relabel=True`` also returns new_of_old [n] (int64, device) from the
+    generator's ids to the ids used here, for callers that hold data in the generator's order)."""
     from . import _lib
     lib = _lib.load()
     if stripes == 0:
         stripes = auto_stripes(n, world)
+    striped = world > 1 and stripes > 1 and n % (world * stripes) == 0
 
-    def keys_of(e0, e1):
+    def keys_of(e0, e1, second=None):
         k = torch.empty(2 * (e1 - e0), dtype=torch.int64, device=dev)
         rc = lib.ppnp_rmat_keys(int(seed), int(scale), int(n), int(e0), int(e1), _lib.ptr(k), _lib.current_stream())
         _lib.check(rc, "ppnp_rmat_keys")
         k = k[k >= 0]
-        if world > 1 and stripes > 1 and n % (world * stripes) == 0:
-            k = (stripe_relabel(k >> 32, n, world, stripes) << 32) | stripe_relabel(k & 0xFFFFFFFF, n, world, stripes)
+        if striped or second is not None:
+            r, c = k >> 32, k & 0xFFFFFFFF
+            if striped:
+                r, c = stripe_relabel(r, n, world, stripes), stripe_relabel(c, n, world, stripes)
+            if second is not None:
+                r, c = second[r], second[c]
+            k = (r << 32) | c
         return k
 
     # pass 1: this rank histograms its slice of the draws, all-reduce -> approximate degrees
@@ -1325,13 +1352,14 @@ def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group
     w += w_part
     del w_part
     bounds = balanced_row_blocks(w, world)
+    second = degree_sort_relabel(w, bounds) if degree_sort else None
     del w
     lo, hi = bounds[rank], bounds[rank + 1]
     # pass 2: all draws, keep my rows
     kept = [(torch.arange(lo, hi, device=dev, dtype=torch.int64) << 32) | torch.arange(lo, hi, device=dev, dtype=torch.int64)]
     pending = 0
     for e0 in range(0, raw_draws, batch):
-        k = keys_of(e0, min(raw_draws, e0 + batch))
+        k = keys_of(e0, min(raw_draws, e0 + batch), second)
         k = k[(k >= (lo << 32)) & (k < (hi << 32))]
         kept.append(k)
         pending += k.numel()
@@ -1346,6 +1374,12 @@ def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group
     counts = torch.bincount(rows, minlength=hi - lo)
     indptr = torch.zeros(hi - lo + 1, dtype=torch.int64, device=dev)
     indptr[1:] = torch.cumsum(counts, 0)
+    if return_relabel:
+        ids = torch.arange(n, device=dev, dtype=torch.int64)
+        new_of_old = stripe_relabel(ids, n, world, stripes) if striped else ids
+        if second is not None:
+            new_of_old = second[new_of_old]
+        return indptr, cols, bounds, new_of_old
     return indptr, cols, bounds
 
 
@@ -1369,14 +1403,15 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
 
 
 def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4,
-                      carve=None, hub_degree=64, idx16=False, check_small=None, rows_below=None, rows_order="dest", window=None):
+                      carve=None, hub_degree=64, idx16=False, check_small=None, rows_below=None, rows_order="dest", window=None,
+                      degree_sort=True):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
     t0 = time.perf_counter()
     if stripes == 0:
         stripes = auto_stripes(n, world)
-    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world, stripes=stripes)
+    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world, stripes=stripes, degree_sort=degree_sort)
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
@@ -1579,7 +1614,8 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
     return {
         "parity": parity,
         "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,
-        "partition": {"rule": f"block-cyclic relabelling ({stripes} stripes per rank), then contiguous row blocks cut at the non-zero prefix sum", "phases": prop.phases,
+        "partition": {"rule": f"block-cyclic relabelling ({stripes} stripes per rank), then contiguous row blocks cut at the non-zero prefix sum"
+                              + (", rows of a block stored in degree order" if degree_sort else ""), "phases": prop.phases,
                       "transport": prop.transport_name,
                       "rows": [int(s[2]) for s in allstats], "nnz": [int(s[0]) for s in allstats],
                       "halo_rows": [int(s[1]) for s in allstats], "interior_rows": [int(s[3]) for s in allstats],

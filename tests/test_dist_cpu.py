@@ -156,3 +156,19 @@ def test_stripe_relabel_is_a_bijection_that_mixes_the_id_space():
             assert old_in_first.max() > 0.9 * n and abs(float(old_in_first.float().mean()) / n - 0.5) < 0.1
     assert auto_stripes(1000, 1) == 1 and auto_stripes(1001, 2) == 1      # nothing to deal / not divisible
     assert torch.equal(stripe_relabel(torch.arange(10), 10, 1, 4), torch.arange(10))
+
+
+def test_degree_sort_relabel_keeps_blocks_and_orders_them_by_weight():
+    from ppnp_b200.dist import degree_sort_relabel
+    g = torch.Generator().manual_seed(0)
+    w = torch.randint(1, 50, (1000,), generator=g, dtype=torch.int32)
+    bounds = [0, 130, 130, 700, 1000]                      # an empty block in the middle
+    f = degree_sort_relabel(w, bounds)
+    assert torch.equal(torch.sort(f).values, torch.arange(1000))           # a bijection
+    old_of_new = torch.argsort(f)
+    for lo, hi in zip(bounds, bounds[1:]):
+        assert bool(((f[lo:hi] >= lo) & (f[lo:hi] < hi)).all())            # nobody leaves its block
+        ws = w[old_of_new[lo:hi]]
+        assert bool((ws[1:] <= ws[:-1]).all())                             # descending weight inside the block ...
+        same = ws[1:] == ws[:-1]
+        assert bool((old_of_new[lo:hi][1:][same] > old_of_new[lo:hi][:-1][same]).all())   # ... ties by id

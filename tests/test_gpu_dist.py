@@ -22,7 +22,7 @@ def worker(rank, world, port, mode, outdir):
     try:
         from ppnp_b200 import dist as pd
         n, raw, scale, F, K, alpha = 204_800, 3_000_000, 18, 16, 10, 0.1   # multiple of world * 16 stripes
-        indptr, cols, bounds = pd.rmat_shard(n, raw, scale, 0, dev, rank, world, batch=1 << 20)
+        indptr, cols, bounds, relabel = pd.rmat_shard(n, raw, scale, 0, dev, rank, world, batch=1 << 20, return_relabel=True)
         dinv = pd.global_dinv(indptr, bounds, rank, world, dev)
         topo = pd.build_shard_topology(indptr, cols, bounds, rank)
         phases, transport = mode.split("/")
@@ -44,7 +44,7 @@ def worker(rank, world, port, mode, outdir):
             prop = pd.PartitionedPropagation(topo, dinv, phases=phases, transport=transport)
         lo, hi = bounds[rank], bounds[rank + 1]
         # rows are the striped relabelling of the generator's ids: new id -> old id
-        new_of_old = pd.stripe_relabel(torch.arange(n), n, world, pd.auto_stripes(n, world)).numpy()
+        new_of_old = relabel.cpu().numpy()
         old_of_new = np.argsort(new_of_old)
         mine = old_of_new[lo:hi]
         Hg = np.random.RandomState(0).randn(n, F).astype(np.float32)
