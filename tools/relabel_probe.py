@@ -49,7 +49,24 @@ def main():
     order = torch.sort(deg, descending=True, stable=True).indices
     by_deg = torch.empty(n, dtype=torch.int64, device=dev); by_deg[order] = torch.arange(n, device=dev)
     labels["ids by descending degree"] = by_deg
-    labels["random ids"] = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    if os.environ.get("PROBE_RANDOM"):
+        labels["random ids"] = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    # hot rows by degree; cold rows grouped by their highest-degree neighbour (in that neighbour's degree rank), so that
+    # the cold columns a hub row gathers are CONSECUTIVE rows of Z
+    rows = torch.repeat_interleave(torch.arange(n, device=dev), deg)
+    cand = (deg[idx.long()] << 32) | (0xFFFFFFFF - idx.long())
+    best = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    best.scatter_reduce_(0, rows, cand, reduce="amax", include_self=True)
+    del rows, cand
+    hub = torch.where(best >= 0, 0xFFFFFFFF - (best & 0xFFFFFFFF), torch.arange(n, device=dev))
+    hub_rank = torch.where(best >= 0, by_deg[hub], torch.full_like(hub, n))
+    for T in (16, 64, 256):
+        hot = deg >= T
+        k1 = torch.where(hot, torch.zeros_like(hub_rank), hub_rank + 1)          # hot block first, then by the hub's rank
+        k2 = by_deg                                                                 # inside a group: by own degree rank
+        o = torch.sort(k1 * n + k2).indices                                          # (n + 1) * n < 2^63
+        f = torch.empty(n, dtype=torch.int64, device=dev); f[o] = torch.arange(n, device=dev)
+        labels[f"hot (deg >= {T}) by degree, cold grouped by their best hub"] = f
     for name, f in labels.items():
         a_ip, a_idx = (ip, idx) if f is None else relabel(ip, idx, f)
         ahat = P.csr_normalize(a_ip.to(torch.int32) if int(a_ip[-1]) < 2**31 else a_ip, a_idx)
