@@ -589,7 +589,7 @@ def run_ours(args):
                                                "min_piece": args.carve_min_piece} if args.order == "carve" else None),
                                        rows_below=(args.rows_below or None), rows_order=args.rows_order,
                                        window=(args.window_key if args.order == "window" else None),
-                                       degree_sort=not args.no_degree_sort,
+                                       degree_sort=not args.no_degree_sort, row_cost=args.row_cost,
                                        check_small=(None if args.no_parity else
                                                     (lambda mk, al: parity_small_partitioned(mk, al, dev, rank, world, F, KSTEPS, ALPHA))))
         if rank == 0:
@@ -895,6 +895,8 @@ def main():
     ap.add_argument("--hub-degree", type=int, default=64, help="multi-GPU --transport hybrid: rows of at least this degree are summed where their columns live")
     ap.add_argument("--no-degree-sort", action="store_true", help="partitioned path: keep the generator's order of the rows inside a block "
                     "(default: rows of a block are stored by descending degree, so that hot 64-byte rows share their 128-byte lines)")
+    ap.add_argument("--row-cost", type=float, default=None, help="multi-GPU: weight of a row, in stored entries, added to its non-zeros when the "
+                    "row blocks are cut (default: dist.auto_row_cost; 0 = cut by non-zeros alone)")
     ap.add_argument("--transport", default="auto", choices=["auto", "fused", "hybrid", "pipe", "pull", "push", "p2p"], help="multi-GPU: halo transport")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1309,15 +1309,28 @@ def degree_sort_relabel(w, bounds):
     return new_of_old
 
 
+def auto_row_cost(world):
+    """Cost of a ROW of a shard in units of one stored entry, for the cut of the row blocks: a row costs its teleport
+    read, its result write and its self gather whatever its degree (~4 entries' worth at F = 16) plus the pushes of
+    its result to the peers that reference it (~6 entries' worth each, 1.4 peers per row at 8 ranks).  Fitted to
+    the 8-GPU run of profiles/r02_bench_n8_degree_sorted.jsonl: with the cut by non-zeros alone the last rank owns
+    16.3 M rows and ships 21.7 M (the first: 9.5 M and 15.0 M) and every step waits for it -- 244 M entries + 12.4 x
+    16.3 M rows = 446 M units there against a mean of 398 M."""
+    if world <= 1:
+        return 0.0
+    return 4.0 + 6.0 * 1.6 * (1.0 - 1.0 / world)
+
+
 def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group=None, stripes=0, degree_sort=True,
-               return_relabel=False):
+               return_relabel=False, row_cost=None):
     """Rows of A + I of the R-MAT graph owned by ``rank`` (global column ids) and the partition.
     Pass 1 estimates the per-row weight from the raw draws to place the boundaries by non-zeros;
     pass 2 keeps the (de-duplicated) edges whose row falls inside this rank's block.  Vertex ids
     are the striped relabelling of the generator's ids (``stripe_relabel``) followed, with
     ``degree_sort``, by ``degree_sort_relabel`` inside every block (both are the partitioner's choice of
     row order; ``return_relabel=True`` also returns new_of_old [n] (int64, device) from the
-    generator's ids to the ids used here, for callers that hold data in the generator's order)."""
+    generator's ids to the ids used here, for callers that hold data in the generator's order).
+    ``row_cost``: per-row weight added to the row's non-zeros when the blocks are cut (None: ``auto_row_cost``)."""
     from . import _lib
     lib = _lib.load()
     if stripes == 0:
@@ -1351,7 +1364,8 @@ def rmat_shard(n, raw_draws, scale, seed, dev, rank, world, batch=1 << 26, group
         dist.all_reduce(w_part, group=group)
     w += w_part
     del w_part
-    bounds = balanced_row_blocks(w, world)
+    rc_ = auto_row_cost(world) if row_cost is None else float(row_cost)
+    bounds = balanced_row_blocks(w if rc_ == 0 else w.to(torch.float64) + rc_, world)
     second = degree_sort_relabel(w, bounds) if degree_sort else None
     del w
     lo, hi = bounds[rank], bounds[rank + 1]
@@ -1404,14 +1418,14 @@ def global_dinv(indptr_local, bounds, rank, world, dev, group=None):
 
 def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, world, phases="peer", transport="auto", stripes=0, row_groups=4,
                       carve=None, hub_degree=64, idx16=False, check_small=None, rows_below=None, rows_order="dest", window=None,
-                      degree_sort=True):
+                      degree_sort=True, row_cost=None):
     """bench.py's multi-GPU leg: strong scaling of one pass (K forward + K backward steps) on the
     row-partitioned graph.  Times on the device with CUDA events, max over ranks."""
     import time
     t0 = time.perf_counter()
     if stripes == 0:
         stripes = auto_stripes(n, world)
-    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world, stripes=stripes, degree_sort=degree_sort)
+    indptr, cols, bounds = rmat_shard(n, raw, scale, 0, dev, rank, world, stripes=stripes, degree_sort=degree_sort, row_cost=row_cost)
     dinv = global_dinv(indptr, bounds, rank, world, dev)
     topo = build_shard_topology(indptr, cols, bounds, rank)
     del cols
@@ -1615,6 +1629,7 @@ def bench_partitioned(wl, n, raw, scale, F, K, alpha, steps, warmup, dev, rank, 
         "parity": parity,
         "ms_per_step": float(ms), "nnz": nnz, "clocks": clocks,
         "partition": {"rule": f"block-cyclic relabelling ({stripes} stripes per rank), then contiguous row blocks cut at the non-zero prefix sum"
+                              + f" of (non-zeros + {auto_row_cost(world) if row_cost is None else row_cost:g} per row)"
                               + (", rows of a block stored in degree order" if degree_sort else ""), "phases": prop.phases,
                       "transport": prop.transport_name,
                       "rows": [int(s[2]) for s in allstats], "nnz": [int(s[0]) for s in allstats],
