@@ -611,7 +611,7 @@ def run_ours(args):
                              "peak_source": peak_src + f" x {world} GPUs", "kernel": "spmm_stream_kernel"},
                 "e2e": result.pop("e2e"), "gpu_launches": result.pop("gpu_launches"), "clocks": sampler_clocks,
                 "parity": result.pop("parity"),
-                "extra": dict(result, n1_committed_round1=n1_reference(wl)),
+                "extra": dict(result, n1_committed=n1_reference(wl)),
             }
         dist.barrier()
         dist.destroy_process_group()
