@@ -281,3 +281,19 @@ def test_window_order_is_a_chunk_permutation_of_rank_sorted_rows_with_the_same_r
         # lane transposition composes with it
         wt = lane_transpose(win, 16)
         assert relerr(walk_stream(wt, H, H, 0.1, 0, True), ref) < 1e-7
+
+
+def test_rank_sorted_csr_batches_give_the_same_arrays():
+    """The row-block batching of rank_sorted_csr (bounded temporaries next to a multi-GB shard) must not show in the result."""
+    from ppnp_b200.plan import rank_sorted_csr
+    ah, ip, idx, val = ahat_tensors("citeseer")
+    full = rank_sorted_csr(ip, idx, val)
+    for mb in (1, 7, 100, 5000):            # 1: one row per batch (rows longer than the batch still go whole)
+        part = rank_sorted_csr(ip, idx, val, max_batch_edges=mb)
+        assert torch.equal(part[0], full[0]) and torch.equal(part[1], full[1]) and torch.equal(part[2], full[2])
+    # rectangular column space (a shard: local rows x [local | halo] columns): ranks by reference count
+    n = ah.shape[0]
+    wide = rank_sorted_csr(ip, idx, None, n_cols=n + 50)
+    assert wide[2].numel() == n + 50 and torch.equal(torch.sort(wide[2]).values, torch.arange(n + 50))
+    refs = torch.bincount(idx.to(torch.int64), minlength=n + 50)
+    assert bool((refs[torch.argsort(wide[2])][1:] <= refs[torch.argsort(wide[2])][:-1]).all())
