@@ -3,7 +3,9 @@ R-MAT scale model: (a) block-cyclic stripes + nnz-balanced 
 (b) the generator's natural ids + nnz-balanced contiguous cuts (keeps R-MAT's id-prefix locality, loses balance of the
 SENT volume), (c) natural ids with the k highest-degree rows replicated on every rank (their Z rows are recomputed
 locally from partial sums -- counted as k partial rows received per rank instead of halo rows).
-Prints rows received / sent per rank and step and the nnz balance."""
+Prints rows received / sent per rank and step and the nnz balance.
+(Since the end of round 2 dist.py also weighs rows in the cut -- auto_row_cost, which moves the boundaries by a few per
+cent -- and stores the rows of a block in degree order, which changes no block's membership and hence no halo volume.)"""
 import os
 import sys
 
